@@ -1,0 +1,102 @@
+// Shared device/host helpers for the sketchedit_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+namespace se {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: every C-ABI entry point returns 0 on success, non-zero on failure and leaves
+// a message retrievable through se_last_error().
+void set_error(const std::string& msg);
+const char* last_error();
+
+#define SE_CUDA_OK(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      se::set_error(std::string(#expr) + " -> " + cudaGetErrorString(_e) + " at " + __FILE__ + \
+                    ":" + std::to_string(__LINE__));                                          \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+#define SE_REQUIRE(cond, msg)                                                                 \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      se::set_error(std::string("requirement failed: ") + #cond + " : " + (msg) + " at " +    \
+                    __FILE__ + ":" + std::to_string(__LINE__));                               \
+      return 2;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// tile geometry shared by every convolution kernel: one CTA tile = 8 x 16 output positions
+constexpr int TILE_H = 8;
+constexpr int TILE_W = 16;
+constexpr int TILE_M = TILE_H * TILE_W;  // 128 = UMMA M = TMEM lanes
+constexpr int MAX_TAPS = 32;
+constexpr int KCHUNK = 32;               // bf16 elements per K chunk = 64 B = SWIZZLE_64B span
+
+enum Epilogue : int {
+  EPI_GATE_ELU = 0,   // ELU(y[c]) * sigmoid(y[c + Cout/2])              (reference utils.py:29-32)
+  EPI_GATE_RELU = 1,  // ReLU(y[c]) * sigmoid(y[c + Cout/2])             (pmconv6, editline_g.py:89-90)
+  EPI_LINEAR = 2,     // (y[c] + bias[c]) * scale * colscale[n][c]       (raw conv / attention GEMMs)
+};
+
+enum DType : int { DT_BF16 = 0, DT_F32 = 1 };
+
+// One generalised convolution launch. Positions p=(py,px) on an Ho x Wo grid; input pixel for tap t
+// is (py*stride + dy[t], px*stride + dx[t]) (zero outside the image); output pixel is
+// (py*osy + ooy, px*osx + oox) inside an Hout x Wout image with pixel pitch ldo and channel
+// offset choff. Weights may differ per image (attention), w_img_stride = 0 otherwise.
+struct ConvParams {
+  // input
+  const void* x;        // NHWC, dtype in_dt, pixel pitch ldx elements
+  int in_dt;
+  int N, Hi, Wi, Ci, ldx;
+  // position grid + taps
+  int Ho, Wo, stride;
+  int ntaps;
+  int8_t dy[MAX_TAPS], dx[MAX_TAPS];
+  // weights / bias
+  const void* w;        // layout depends on the kernel (see se_conv_direct.cu / se_conv_tc.cu)
+  long long w_img_stride;   // elements between images (0 = shared)
+  const float* bias;    // [Cout] or nullptr
+  int Cout;             // pre-gate output channels (GEMM N, real)
+  // output
+  void* y;
+  int out_dt;
+  int Hout, Wout, ldo, choff;
+  int osy, ooy, osx, oox;
+  // epilogue
+  int epi;
+  float scale;                  // EPI_LINEAR
+  const float* colscale;        // EPI_LINEAR: [N][Cout] or nullptr
+};
+
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : (__expf(x) - 1.0f); }
+
+__device__ __forceinline__ float gate_act(float f, float g, int epi) {
+  float a = (epi == EPI_GATE_ELU) ? elu1(f) : fmaxf(f, 0.0f);
+  return a * fast_sigmoid(g);
+}
+#endif
+
+}  // namespace se

@@ -1,0 +1,421 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.
+//
+// One persistent CTA per SM. Per output tile (8 x 16 positions of one image = UMMA M = 128) the
+// K loop walks (tap, 32-channel chunk): the A operand is a TMA *tiled* box of the NHWC input shifted
+// by the tap offset (zero padding = TMA out-of-bounds fill; stride-2 = TMA element strides), the
+// B operand is a [NT x 32] K-major slab of the packed weights. Both land in SWIZZLE_64B shared
+// memory and feed tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulating into one of two TMEM
+// accumulator stages; four epilogue warps drain the other stage (tcgen05.ld), apply
+// bias + ELU/ReLU x sigmoid gating (reference models/networks/utils.py:25-33) or the linear
+// epilogue of the attention GEMMs, and store NHWC.
+//
+//   warp 0 : TMA producer (one lane)        warp 1 : MMA issuer (one lane)
+//   warp 2 : TMEM allocator                 warps 4-7 : epilogue (TMEM lane quadrant = warp % 4)
+#include "se_common.cuh"
+#include "se_conv_tc.h"
+
+namespace se {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("se_conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_64B operand tile: rows of 64 B, 8-row atoms 512 B apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address        bits [0,14)
+  d |= (uint64_t)0 << 16;                         // leading byte offset  bits [16,30)  (unused: one atom along K)
+  d |= (uint64_t)(512 >> 4) << 32;                // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version 1 (sm_100)
+  d |= (uint64_t)4 << 61;                         // layout type: SWIZZLE_64B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+constexpr int A_CHUNK_BYTES = TILE_M * KCHUNK * 2;   // 8192
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;                      // TMEM columns between the two accumulator stages
+constexpr int MAX_STAGES = 8;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A kch chunks | B kch chunks] then barriers, tmem ptr, bias
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_chunk_bytes = p.NT * KCHUNK * 2;
+  const int stage_bytes = p.kch * (A_CHUNK_BYTES + b_chunk_bytes);
+  uint8_t* tail = smem + (size_t)p.num_stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // bias (all N tiles) into shared memory; zero when absent
+  for (int i = threadIdx.x; i < p.n_tiles * p.NT + 32; i += NUM_THREADS) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int total_tiles = p.N * tiles_per_img * p.n_tiles;
+  const int groups = p.nchunks / p.kch;
+  const int ksteps = p.ntaps * groups;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================================== TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int rest = tile / p.n_tiles;
+        const int tx = rest % p.tiles_x;
+        rest /= p.tiles_x;
+        const int ty = rest % p.tiles_y;
+        const int img = rest / p.tiles_y;
+        const int x0 = tx * TILE_W * p.stride, y0 = ty * TILE_H * p.stride;
+        const int wrow0 = img * p.w_img_rows + nt * p.NT;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int xs = x0 + p.dx[t], ys = y0 + p.dy[t];
+          for (int g = 0; g < groups; ++g) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            uint8_t* sA = smem + (size_t)stage * stage_bytes;
+            uint8_t* sB = sA + p.kch * A_CHUNK_BYTES;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            for (int j = 0; j < p.kch; ++j) {
+              const int chunk = g * p.kch + j;
+              tma_load_4d(sA + j * A_CHUNK_BYTES, &tmA, &full_bar[stage], chunk * KCHUNK, xs, ys, img);
+              tma_load_2d(sB + j * b_chunk_bytes, &tmB, &full_bar[stage], 0, wrow0 + (t * p.nchunks + chunk) * p.w_rows_tc);
+            }
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================================================== MMA issuer
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sB = sA + p.kch * A_CHUNK_BYTES;
+          for (int j = 0; j < p.kch; ++j) {
+#pragma unroll
+            for (int k = 0; k < KCHUNK / 16; ++k) {
+              const uint64_t adesc = make_kmajor_sw64_desc(sA + j * A_CHUNK_BYTES + k * 32);
+              const uint64_t bdesc = make_kmajor_sw64_desc(sB + j * b_chunk_bytes + k * 32);
+              umma_bf16(tmem_d, adesc, bdesc, idesc, (ks | j | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+          if (ks == ksteps - 1) umma_commit(&tmem_full[as]);    // accumulator complete
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ==================================================================== epilogue
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;             // tile row == TMEM lane == output position in tile
+    const int ry = row / TILE_W, rx = row % TILE_W;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int nt = tile % p.n_tiles;
+      int rest = tile / p.n_tiles;
+      const int tx = rest % p.tiles_x;
+      rest /= p.tiles_x;
+      const int ty = rest % p.tiles_y;
+      const int img = rest / p.tiles_y;
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
+      const int py = ty * TILE_H + ry, px = tx * TILE_W + rx;
+      const bool valid = (py < p.Ho) && (px < p.Wo);
+      const int oy = py * p.osy + p.ooy, ox = px * p.osx + p.oox;
+      const size_t opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
+
+      if (p.epi == EPI_LINEAR) {
+        const int n0 = nt * p.NT;
+        for (int c0 = 0; c0 < p.NT; c0 += 16) {
+          if (n0 + c0 >= p.Cout) break;
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (valid) {
+            const int cnt = min(16, p.Cout - (n0 + c0));
+            const float* cs = p.colscale ? p.colscale + (size_t)img * p.Cout + n0 + c0 : nullptr;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float s = p.scale * ((cs && i < cnt) ? cs[i] : 1.0f);
+              v[i] = (v[i] + bias_s[n0 + c0 + i]) * s;
+            }
+            if (p.out_dt == DT_F32) {
+              float* o = reinterpret_cast<float*>(p.y) + opix * p.ldo + p.choff + n0 + c0;
+              if (cnt == 16) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+                for (int i = 0; i < cnt; ++i) o[i] = v[i];
+              }
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.ldo + p.choff + n0 + c0;
+              if (cnt == 16) {
+                uint4 a = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                uint4 b = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                *reinterpret_cast<uint4*>(o) = a;
+                *reinterpret_cast<uint4*>(o + 8) = b;
+              } else {
+                for (int i = 0; i < cnt; ++i) o[i] = __float2bfloat16(v[i]);
+              }
+            }
+          }
+        }
+      } else {
+        // gated: feature column c pairs with gate column c + half; both live in this thread's lane
+        const int half = p.Cout >> 1;
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.ldo + p.choff;
+        for (int c0 = 0; c0 < half; c0 += 16) {
+          float f[16], g[16];
+          tmem_ld16(taddr + c0, f);
+          tmem_ld16(taddr + half + c0, g);
+          if (valid) {
+            const int cnt = min(16, half - c0);
+            float r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = gate_act(f[i] + bias_s[c0 + i], g[i] + bias_s[half + c0 + i], p.epi);
+            if (cnt == 16) {
+              *reinterpret_cast<uint4*>(o + c0) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+              *reinterpret_cast<uint4*>(o + c0 + 8) = make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15]));
+            } else {
+              for (int i = 0; i + 1 < cnt; i += 2) *reinterpret_cast<uint32_t*>(o + c0 + i) = pack_bf16x2(r[i], r[i + 1]);
+              if (cnt & 1) o[c0 + cnt - 1] = __float2bfloat16(r[cnt - 1]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int g_num_sms = 0;
+static int g_smem_optin = 0;
+
+int tc_smem_budget() { return 200 * 1024; }
+
+int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  SE_REQUIRE(c.in_dt == DT_BF16, "tcgen05 path reads bf16 activations");
+  SE_REQUIRE(c.ldx % 8 == 0, "input pixel pitch must be a multiple of 8 elements (16 B TMA stride)");
+  SE_REQUIRE((reinterpret_cast<uintptr_t>(c.x) & 15) == 0, "input base must be 16 B aligned");
+  SE_REQUIRE(c.ntaps <= MAX_TAPS && c.ntaps == w.ntaps, "tap count mismatch");
+  SE_REQUIRE(w.NT % 16 == 0 && w.NT >= 16 && w.NT <= 256, "NT");
+  SE_REQUIRE(w.nchunks % w.kch == 0, "kch must divide nchunks");
+  SE_REQUIRE(w.nchunks * KCHUNK >= c.Ci, "weights do not cover Ci");
+  SE_REQUIRE(c.stride >= 1 && c.stride <= 2, "stride");
+  p.N = c.N; p.Ho = c.Ho; p.Wo = c.Wo;
+  p.tiles_x = (c.Wo + TILE_W - 1) / TILE_W;
+  p.tiles_y = (c.Ho + TILE_H - 1) / TILE_H;
+  p.n_tiles = w.n_tiles;
+  p.stride = c.stride;
+  p.ntaps = c.ntaps;
+  memcpy(p.dy, c.dy, sizeof(p.dy));
+  memcpy(p.dx, c.dx, sizeof(p.dx));
+  p.nchunks = w.nchunks; p.kch = w.kch; p.NT = w.NT;
+  p.w_rows_tc = w.n_tiles * w.NT;
+  p.w_img_rows = w.img_rows;
+  p.bias = c.bias; p.Cout = c.Cout;
+  p.y = c.y; p.out_dt = c.out_dt; p.Hout = c.Hout; p.Wout = c.Wout; p.ldo = c.ldo; p.choff = c.choff;
+  p.osy = c.osy; p.ooy = c.ooy; p.osx = c.osx; p.oox = c.oox;
+  p.epi = c.epi; p.scale = c.scale; p.colscale = c.colscale;
+  if (c.epi != EPI_LINEAR) {
+    SE_REQUIRE(w.n_tiles == 1 && c.Cout % 2 == 0 && c.out_dt == DT_BF16, "gated epilogue needs one N tile, even Cout, bf16 out");
+  }
+  const int stage_bytes = w.kch * (A_CHUNK_BYTES + w.NT * KCHUNK * 2);
+  int stages = tc_smem_budget() / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  SE_REQUIRE(stages >= 2, "pipeline needs >= 2 stages");
+  p.num_stages = stages;
+  *smem_bytes = 1024 + stages * stage_bytes + (2 * MAX_STAGES + 4) * 8 + 16 + (p.n_tiles * p.NT + 32) * 4 + 64;
+  *out = p;
+  return 0;
+}
+
+int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
+  TcParams p;
+  int smem_bytes = 0;
+  int rc = tc_plan(c, w, &p, &smem_bytes);
+  if (rc) return rc;
+  EncodeTiledFn enc = get_encode_fn();
+  SE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  if (!g_num_sms) {
+    int dev = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    SE_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    SE_CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+  }
+  SE_REQUIRE(smem_bytes <= g_smem_optin, "shared memory plan exceeds the opt-in limit");
+
+  CUtensorMap tmA, tmB;
+  {
+    // activations: (C, W, H, N), box (32, 16*s, 8*s, 1) walked with element strides (1, s, s, 1)
+    cuuint64_t dims[4] = {(cuuint64_t)c.Ci, (cuuint64_t)c.Wi, (cuuint64_t)c.Hi, (cuuint64_t)c.N};
+    cuuint64_t strides[3] = {(cuuint64_t)c.ldx * 2, (cuuint64_t)c.Wi * c.ldx * 2, (cuuint64_t)c.Hi * c.Wi * c.ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KCHUNK, (cuuint32_t)(TILE_W * c.stride), (cuuint32_t)(TILE_H * c.stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed, CUresult=" + std::to_string((int)r));
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)KCHUNK, (cuuint64_t)w.total_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)KCHUNK * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KCHUNK, (cuuint32_t)w.NT};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w.data), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed, CUresult=" + std::to_string((int)r));
+  }
+  const int total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_tiles;
+  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace se

@@ -1,0 +1,927 @@
+// Host side of the library: weight packing, the generator forward graph, the C ABI
+// (include/sketchedit_b200.h). Graph structure follows
+//   MDGenerator.forward            reference models/networks/editline2_g.py:59-94
+//   DeepFillC2Generator.forward    reference models/networks/editline_g.py:119-221
+//   EditLine2Model inference       reference models/editline2_model.py:128-133,338-370
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sketchedit_b200.h"
+#include "se_common.cuh"
+#include "se_conv_direct.h"
+#include "se_conv_tc.h"
+#include "se_misc.h"
+
+namespace se {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+
+static thread_local int g_launches = 0;
+
+// ------------------------------------------------------------------------------------------ tc timing
+static bool g_tc_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_pool;
+static size_t g_ev_used = 0;
+static double g_tc_flops = 0.0;
+
+// ------------------------------------------------------------------------------------------ architecture
+struct Spec {
+  const char* name;
+  int cin, cout, k, stride, rate;
+  bool deconv;
+  int act;   // 0 elu, 1 relu, -1 none
+};
+
+static std::vector<Spec> encoder(const std::string& pfx, int cin0, std::vector<std::string>& names) {
+  const int c = 48;
+  struct R { const char* n; int ci, co, k, s, r; };
+  const R rows[10] = {{"conv1", cin0, c, 5, 1, 1},          {"conv2_downsample", c / 2, 2 * c, 3, 2, 1},
+                      {"conv3", c, 2 * c, 3, 1, 1},         {"conv4_downsample", c, 4 * c, 3, 2, 1},
+                      {"conv5", 2 * c, 4 * c, 3, 1, 1},     {"conv6", 2 * c, 4 * c, 3, 1, 1},
+                      {"conv7_atrous", 2 * c, 4 * c, 3, 1, 2},  {"conv8_atrous", 2 * c, 4 * c, 3, 1, 4},
+                      {"conv9_atrous", 2 * c, 4 * c, 3, 1, 8},  {"conv10_atrous", 2 * c, 4 * c, 3, 1, 16}};
+  std::vector<Spec> v;
+  for (auto& r : rows) {
+    names.push_back(pfx + r.n);
+    v.push_back(Spec{nullptr, r.ci, r.co, r.k, r.s, r.r, false, 0});
+  }
+  return v;
+}
+
+struct ArchTable {
+  std::vector<std::string> names;
+  std::vector<Spec> specs;
+  void add(const std::string& n, int ci, int co, int k = 3, int s = 1, int r = 1, bool deconv = false, int act = 0) {
+    if (co == 3) act = -1;   // reference utils.py:27
+    names.push_back(n);
+    specs.push_back(Spec{nullptr, ci, co, k, s, r, deconv, act});
+  }
+  void add_encoder(const std::string& pfx, int cin0) {
+    std::vector<std::string> nn;
+    auto v = encoder(pfx, cin0, nn);
+    for (size_t i = 0; i < v.size(); ++i) { names.push_back(nn[i]); specs.push_back(v[i]); }
+  }
+  void add_decoder(const std::string& pfx, int cin11, int cout17) {
+    const int c = 48;
+    add(pfx + "11", cin11, 4 * c);
+    add(pfx + "12", 2 * c, 4 * c);
+    add(pfx + "13_upsample_conv", 2 * c, 2 * c, 3, 1, 1, true);
+    add(pfx + "14", c, 2 * c);
+    add(pfx + "15_upsample_conv", c, c, 3, 1, 1, true);
+    add(pfx + "16", c / 2, c / 2);
+    add(pfx + "17", c / 4, cout17, 3, 1, 1, false, -1);
+  }
+};
+
+static ArchTable make_arch(char net) {
+  ArchTable t;
+  const int c = 48;
+  if (net == 'M') {
+    t.add_encoder("", 4);
+    t.add_decoder("conv", 2 * c, 3);
+    t.add_decoder("conv_mask_", 2 * c, 1);
+  } else {
+    t.add_encoder("", 5);
+    t.add_decoder("conv", 4 * c, 3);
+    t.add_encoder("w", 5);
+    t.add("xconv1", 3, c, 5);
+    t.add("xconv2_downsample", c / 2, c, 3, 2);
+    t.add("xconv3", c / 2, 2 * c);
+    t.add("xconv4_downsample", c, 2 * c, 3, 2);
+    t.add("xconv5", c, 4 * c);
+    t.add("xconv6", 2 * c, 4 * c);
+    t.add("xconv7_atrous", 2 * c, 4 * c, 3, 1, 2);
+    t.add("xconv8_atrous", 2 * c, 4 * c, 3, 1, 4);
+    t.add("xconv9_atrous", 2 * c, 4 * c, 3, 1, 8);
+    t.add("xconv10_atrous", 2 * c, 4 * c, 3, 1, 16);
+    t.add("pmconv1", 3, c, 5);
+    t.add("pmconv2_downsample", c / 2, c, 3, 2);
+    t.add("pmconv3", c / 2, 2 * c);
+    t.add("pmconv4_downsample", c, 4 * c, 3, 2);
+    t.add("pmconv5", 2 * c, 4 * c);
+    t.add("pmconv6", 2 * c, 4 * c, 3, 1, 1, false, 1);   // ReLU gate, editline_g.py:89-90
+    t.add("pmconv9", 2 * c, 4 * c);
+    t.add("pmconv10", 2 * c, 4 * c);
+    t.add_decoder("allconv", 4 * c, 3);
+  }
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------ packed layers
+struct ClassW {
+  int ntaps = 0;
+  int8_t dy[MAX_TAPS], dx[MAX_TAPS];
+  float* w_direct = nullptr;   // device fp32 [tap][Ci][CoutP]
+  int CoutP = 0;
+  TcWeights tc;                // device bf16
+  bool has_tc = false;
+  int osy = 1, ooy = 0, osx = 1, oox = 0;
+};
+
+struct Layer {
+  Spec spec;
+  std::string name;
+  int Ci = 0;                  // stored input channels (stems are packed to 8)
+  bool is_head = false;
+  bool set = false;
+  std::vector<float> w_host, b_host;
+  std::vector<ClassW> cls;
+  float* bias = nullptr;       // device [cout]
+  float* w_head = nullptr;     // device [9][12][cout] (heads)
+};
+
+}  // namespace se
+
+using namespace se;
+
+struct se_model {
+  std::map<std::string, Layer> layers;   // key = net + "." + name
+  int opt[8] = {1, 0, 0, 0, 1, 0, 0, 0};
+  bool finalized = false;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<void*> owned;              // device allocations of packed weights
+};
+
+namespace se {
+
+static int stored_ci(const Spec& s) { return s.k == 5 ? 8 : s.cin; }
+
+static int upload(se_model* m, const void* host, size_t bytes, void** dev) {
+  SE_CUDA_OK(cudaMalloc(dev, bytes));
+  m->owned.push_back(*dev);
+  SE_CUDA_OK(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// effective tap = sum of source taps (ky,kx) of the OIHW kernel (deconv parity classes merge taps)
+struct EffTap { int dy, dx; std::vector<std::pair<int, int>> src; };
+
+static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, ClassW& cw) {
+  const Spec& s = L.spec;
+  const int Ci = L.Ci, Cout = s.cout, k = s.k;
+  cw.ntaps = (int)taps.size();
+  SE_REQUIRE(cw.ntaps <= MAX_TAPS, "too many taps");
+  cw.CoutP = (Cout + 3) / 4 * 4;
+  std::vector<float> weff((size_t)cw.ntaps * Ci * Cout, 0.0f);
+  for (int t = 0; t < cw.ntaps; ++t) {
+    cw.dy[t] = (int8_t)taps[t].dy;
+    cw.dx[t] = (int8_t)taps[t].dx;
+    for (auto& sk : taps[t].src)
+      for (int ci = 0; ci < s.cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+          weff[((size_t)t * Ci + ci) * Cout + co] += L.w_host[(((size_t)co * s.cin + ci) * k + sk.first) * k + sk.second];
+  }
+  {
+    std::vector<float> wd((size_t)cw.ntaps * Ci * cw.CoutP, 0.0f);
+    for (int t = 0; t < cw.ntaps; ++t)
+      for (int ci = 0; ci < Ci; ++ci)
+        for (int co = 0; co < Cout; ++co) wd[((size_t)t * Ci + ci) * cw.CoutP + co] = weff[((size_t)t * Ci + ci) * Cout + co];
+    int rc = upload(m, wd.data(), wd.size() * 4, (void**)&cw.w_direct);
+    if (rc) return rc;
+  }
+  cw.has_tc = (Ci % 8 == 0) && !L.is_head;
+  if (cw.has_tc) {
+    TcWeights& tc = cw.tc;
+    tc.ntaps = cw.ntaps;
+    tc.nchunks = (Ci + KCHUNK - 1) / KCHUNK;
+    tc.kch = tc.nchunks <= 3 ? tc.nchunks : 3;
+    SE_REQUIRE(tc.nchunks % tc.kch == 0, "chunk grouping");
+    tc.NT = (Cout + 15) / 16 * 16;
+    tc.n_tiles = 1;
+    tc.img_rows = 0;
+    tc.total_rows = (long long)tc.ntaps * tc.nchunks * tc.NT;
+    std::vector<uint16_t> wt((size_t)tc.total_rows * KCHUNK, 0);
+    for (int t = 0; t < tc.ntaps; ++t)
+      for (int ch = 0; ch < tc.nchunks; ++ch)
+        for (int n = 0; n < Cout; ++n)
+          for (int kk = 0; kk < KCHUNK; ++kk) {
+            const int ci = ch * KCHUNK + kk;
+            if (ci < Ci) wt[(((size_t)t * tc.nchunks + ch) * tc.NT + n) * KCHUNK + kk] = f32_to_bf16_rn(weff[((size_t)t * Ci + ci) * Cout + n]);
+          }
+    void* d = nullptr;
+    int rc = upload(m, wt.data(), wt.size() * 2, &d);
+    if (rc) return rc;
+    tc.data = d;
+  }
+  return 0;
+}
+
+static int pack_layer(se_model* m, Layer& L) {
+  const Spec& s = L.spec;
+  L.Ci = stored_ci(s);
+  L.is_head = (s.cin == 12);
+  int rc = upload(m, L.b_host.data(), L.b_host.size() * 4, (void**)&L.bias);
+  if (rc) return rc;
+  if (L.is_head) {
+    std::vector<float> wh((size_t)9 * 12 * s.cout);
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < 12; ++c)
+        for (int o = 0; o < s.cout; ++o) wh[((size_t)t * 12 + c) * s.cout + o] = L.w_host[(((size_t)o * 12 + c) * 3 + t / 3) * 3 + t % 3];
+    rc = upload(m, wh.data(), wh.size() * 4, (void**)&L.w_head);
+    if (rc) return rc;
+  }
+  if (!s.deconv) {
+    std::vector<EffTap> taps;
+    const int p = s.rate * (s.k - 1) / 2;   // reference utils.py:21
+    for (int ky = 0; ky < s.k; ++ky)
+      for (int kx = 0; kx < s.k; ++kx) taps.push_back(EffTap{ky * s.rate - p, kx * s.rate - p, {{ky, kx}}});
+    L.cls.resize(1);
+    return pack_class(m, L, taps, L.cls[0]);
+  }
+  // nearest x2 upsample + 3x3 conv == four sub-pixel 2x2 convs over the low-res map with merged taps:
+  // output row 2i   reads rows {i-1: W[0], i: W[1]+W[2]};  row 2i+1 reads {i: W[0]+W[1], i+1: W[2]}
+  L.cls.resize(4);
+  for (int pc = 0; pc < 4; ++pc) {
+    const int py = pc / 2, px = pc % 2;
+    std::vector<EffTap> taps;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        EffTap e;
+        e.dy = (py == 0) ? (a - 1) : a;
+        e.dx = (px == 0) ? (b - 1) : b;
+        std::vector<int> rows = (py == 0) ? (a == 0 ? std::vector<int>{0} : std::vector<int>{1, 2})
+                                          : (a == 0 ? std::vector<int>{0, 1} : std::vector<int>{2});
+        std::vector<int> cols = (px == 0) ? (b == 0 ? std::vector<int>{0} : std::vector<int>{1, 2})
+                                          : (b == 0 ? std::vector<int>{0, 1} : std::vector<int>{2});
+        for (int r : rows)
+          for (int c : cols) e.src.push_back({r, c});
+        taps.push_back(e);
+      }
+    ClassW& cw = L.cls[pc];
+    cw.osy = 2; cw.ooy = py; cw.osx = 2; cw.oox = px;
+    rc = pack_class(m, L, taps, cw);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ arena
+// Offsets inside one device slab, first-fit with coalescing. The forward graph is replayed twice per
+// call: a dry pass (no launches) finds the peak, then the slab is grown if needed and the real pass runs.
+struct Arena {
+  struct Blk { size_t off, size; };
+  std::vector<Blk> free_list;
+  size_t top = 0, peak = 0;
+  char* base = nullptr;
+  void reset(char* b) { free_list.clear(); top = 0; peak = 0; base = b; }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    for (size_t i = 0; i < free_list.size(); ++i)
+      if (free_list[i].size >= bytes) {
+        size_t off = free_list[i].off;
+        if (free_list[i].size == bytes) free_list.erase(free_list.begin() + i);
+        else { free_list[i].off += bytes; free_list[i].size -= bytes; }
+        return base + off;
+      }
+    size_t off = top;
+    top += bytes;
+    if (top > peak) peak = top;
+    return base + off;
+  }
+  void release(void* p, size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    size_t off = (char*)p - base;
+    if (off + bytes == top) {
+      top = off;
+      // merge trailing free blocks
+      bool again = true;
+      while (again) {
+        again = false;
+        for (size_t i = 0; i < free_list.size(); ++i)
+          if (free_list[i].off + free_list[i].size == top) { top = free_list[i].off; free_list.erase(free_list.begin() + i); again = true; break; }
+      }
+      return;
+    }
+    free_list.push_back({off, bytes});
+    // coalesce neighbours
+    bool again = true;
+    while (again) {
+      again = false;
+      for (size_t i = 0; i < free_list.size() && !again; ++i)
+        for (size_t j = 0; j < free_list.size(); ++j)
+          if (i != j && free_list[i].off + free_list[i].size == free_list[j].off) {
+            free_list[i].size += free_list[j].size;
+            free_list.erase(free_list.begin() + j);
+            again = true;
+            break;
+          }
+    }
+  }
+};
+
+struct Buf { void* p = nullptr; size_t bytes = 0; };
+
+struct Ctx {
+  se_model* m;
+  cudaStream_t stream;
+  int prec;
+  bool dry;
+  Arena arena;
+  int B;
+  int rc = 0;
+  int act_dt() const { return prec == SE_PREC_FP32_EXACT ? DT_F32 : DT_BF16; }
+  size_t esz() const { return prec == SE_PREC_FP32_EXACT ? 4 : 2; }
+  Buf get(size_t bytes) { Buf b; b.bytes = bytes; b.p = arena.alloc(bytes); return b; }
+  void put(Buf& b) { if (b.p) arena.release(b.p, b.bytes); b.p = nullptr; }
+};
+
+#define CK(expr)                      \
+  do {                                \
+    if (!c.dry) {                     \
+      int _rc = (expr);               \
+      if (_rc) { c.rc = _rc; return _rc; } \
+      ++g_launches;                   \
+    }                                 \
+  } while (0)
+
+struct View { void* p; int H, W, C, ld; };   // NHWC activation view (channels [0,C) at pitch ld)
+
+static Layer* find_layer(se_model* m, char net, const std::string& name) {
+  auto it = m->layers.find(std::string(1, net) + "." + name);
+  return it == m->layers.end() ? nullptr : &it->second;
+}
+
+static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw, double flops) {
+  if (c.prec == SE_PREC_BF16_TC && cw.has_tc) {
+    if (g_tc_timing) {
+      if (g_ev_used == g_ev_pool.size()) {
+        cudaEvent_t a, b;
+        SE_CUDA_OK(cudaEventCreate(&a));
+        SE_CUDA_OK(cudaEventCreate(&b));
+        g_ev_pool.push_back({a, b});
+      }
+      auto& ev = g_ev_pool[g_ev_used++];
+      SE_CUDA_OK(cudaEventRecord(ev.first, c.stream));
+      int rc = tc_launch(cp, cw.tc, c.stream);
+      if (rc) return rc;
+      SE_CUDA_OK(cudaEventRecord(ev.second, c.stream));
+      g_tc_flops += flops;
+      return 0;
+    }
+    return tc_launch(cp, cw.tc, c.stream);
+  }
+  ConvParams d = cp;
+  d.w = cw.w_direct;
+  return direct_launch(d, cw.CoutP, c.prec == SE_PREC_FP32_EXACT, c.stream);
+}
+
+// one gated conv / deconv layer: in (Hi x Wi x Ci) -> out view (channels written at [choff, choff+cout_g))
+static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int choff) {
+  const Spec& s = L.spec;
+  const int Ho = s.deconv ? in.H : (in.H + s.stride - 1) / s.stride;   // position grid
+  const int Wo = s.deconv ? in.W : (in.W + s.stride - 1) / s.stride;
+  for (auto& cw : L.cls) {
+    ConvParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.x = in.p; cp.in_dt = c.act_dt();
+    cp.N = c.B; cp.Hi = in.H; cp.Wi = in.W; cp.Ci = L.Ci; cp.ldx = in.ld;
+    cp.Ho = Ho; cp.Wo = Wo; cp.stride = s.deconv ? 1 : s.stride;
+    cp.ntaps = cw.ntaps;
+    memcpy(cp.dy, cw.dy, sizeof(cp.dy));
+    memcpy(cp.dx, cw.dx, sizeof(cp.dx));
+    cp.w = nullptr; cp.w_img_stride = 0;
+    cp.bias = L.bias; cp.Cout = s.cout;
+    cp.y = out; cp.out_dt = c.act_dt();
+    cp.Hout = Ho * cw.osy; cp.Wout = Wo * cw.osx; cp.ldo = ldo; cp.choff = choff;
+    cp.osy = cw.osy; cp.ooy = cw.ooy; cp.osx = cw.osx; cp.oox = cw.oox;
+    cp.epi = s.act == 1 ? EPI_GATE_RELU : EPI_GATE_ELU;
+    cp.scale = 1.0f; cp.colscale = nullptr;
+    const double flops = 2.0 * c.B * Ho * Wo * (double)s.cout * s.cin * (s.deconv ? 9.0 / 4.0 : (double)s.k * s.k);
+    CK(launch_conv(c, cp, cw, flops));
+  }
+  return 0;
+}
+
+static void out_dims(const Spec& s, int H, int W, int* Ho, int* Wo) {
+  if (s.deconv) { *Ho = 2 * H; *Wo = 2 * W; }
+  else { *Ho = (H + s.stride - 1) / s.stride; *Wo = (W + s.stride - 1) / s.stride; }
+}
+
+// run a chain of gated layers; intermediate buffers come from the arena. The last layer writes to
+// (final_out, final_ld, final_choff) when given, else to a fresh buffer returned in *res.
+static int run_chain(Ctx& c, char net, const std::vector<std::string>& names, View in, bool free_in, Buf in_buf, View* res, Buf* res_buf,
+                     void* final_out = nullptr, int final_ld = 0, int final_choff = 0) {
+  View cur = in;
+  Buf cur_buf = in_buf;
+  bool cur_owned = free_in;
+  for (size_t i = 0; i < names.size(); ++i) {
+    Layer* L = find_layer(c.m, net, names[i]);
+    SE_REQUIRE(L != nullptr, "unknown layer " + names[i]);
+    int Ho, Wo;
+    out_dims(L->spec, cur.H, cur.W, &Ho, &Wo);
+    const int cg = L->spec.cout / 2;
+    const bool last = (i + 1 == names.size());
+    View nxt;
+    Buf nb;
+    if (last && final_out) {
+      nxt = View{final_out, Ho, Wo, cg, final_ld};
+      int rc = run_layer(c, *L, cur, final_out, final_ld, final_choff);
+      if (rc) return rc;
+    } else {
+      nb = c.get((size_t)c.B * Ho * Wo * cg * c.esz());
+      nxt = View{nb.p, Ho, Wo, cg, cg};
+      int rc = run_layer(c, *L, cur, nb.p, cg, 0);
+      if (rc) return rc;
+    }
+    if (cur_owned) c.put(cur_buf);
+    cur = nxt;
+    cur_buf = nb;
+    cur_owned = !(last && final_out);
+  }
+  if (res) *res = cur;
+  if (res_buf) *res_buf = cur_buf;
+  return 0;
+}
+
+static std::vector<std::string> with_prefix(const std::string& pfx, std::initializer_list<const char*> l) {
+  std::vector<std::string> v;
+  for (auto s : l) v.push_back(pfx + s);
+  return v;
+}
+
+static int run_head(Ctx& c, char net, const std::string& name, const View& in, int mode, const float* img, const float* mask_bin,
+                    const float* mask_soft, float* out_nchw, float* out2, void* out_pack8) {
+  Layer* L = find_layer(c.m, net, name);
+  SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name);
+  CK(head(in.p, c.act_dt(), L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
+          out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], c.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ contextual attention
+// cam_1 + cam_2 (reference splitcam.py:57-108,147-174) on an NHWC feature map f [B,h,w,C]:
+//   S = Q K^T  as a stride-2, 4x4-tap "convolution" of f with per-image kernels K   (utils.py:72-99)
+//   A = softmax_l(10 * S * m_l),  out = fold_sum(A V) as four sub-pixel 2x2 convolutions over A
+static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int out_ld, float* attn_out /*fp32 [B,L,N] or null*/) {
+  const int B = c.B, h = f.H, w = f.W, C = f.C;
+  SE_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "attention map must be even-sized and >= 4");
+  const int hs = (h - 4) / 2 + 1, ws = (w - 4) / 2 + 1, L = hs * ws;
+  const int Lpad = (L + 255) / 256 * 256;
+  const bool tc = (c.prec == SE_PREC_BF16_TC) && (C % 32 == 0) && (f.ld % 8 == 0);
+  const int dt = c.act_dt();
+
+  Buf rnorm = c.get((size_t)B * C * 4);
+  Buf colm = c.get((size_t)B * L * 4);
+  CK(plane_reduce(f.p, dt, B, h * w, C, f.ld, RED_RNORM, (float*)rnorm.p, c.stream));
+  CK(cam_colmask(mask_s, (float*)colm.p, B, h, w, hs, ws, 0.1f, c.stream));
+
+  // ---- keys
+  const size_t kelems = (size_t)B * 16 * C * Lpad;
+  Buf kbuf = c.get(kelems * (tc ? 2 : 4));
+  SE_REQUIRE(f.ld == C, "attention input must be dense NHWC");
+  CK(cam_pack_k(f.p, dt, (const float*)rnorm.p, kbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, c.stream));
+
+  // ---- logits S[b, n, l] (fp32, row pitch Lpad), scaled by 10 * m_l in the GEMM epilogue
+  Buf sbuf = c.get((size_t)B * L * Lpad * 4);
+  {
+    ConvParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.x = f.p; cp.in_dt = dt; cp.N = B; cp.Hi = h; cp.Wi = w; cp.Ci = C; cp.ldx = f.ld;
+    cp.Ho = hs; cp.Wo = ws; cp.stride = 2; cp.ntaps = 16;
+    for (int t = 0; t < 16; ++t) { cp.dy[t] = (int8_t)(t / 4); cp.dx[t] = (int8_t)(t % 4); }
+    cp.bias = nullptr; cp.Cout = L;
+    cp.y = sbuf.p; cp.out_dt = DT_F32; cp.Hout = hs; cp.Wout = ws; cp.ldo = Lpad; cp.choff = 0;
+    cp.osy = 1; cp.ooy = 0; cp.osx = 1; cp.oox = 0;
+    cp.epi = EPI_LINEAR; cp.scale = 10.0f; cp.colscale = (const float*)colm.p;
+    ClassW cw;
+    cw.ntaps = 16;
+    cw.CoutP = Lpad;
+    cw.w_direct = (float*)kbuf.p;
+    cw.has_tc = tc;
+    cw.tc.data = kbuf.p; cw.tc.ntaps = 16; cw.tc.nchunks = C / 32; cw.tc.kch = (C / 32) <= 3 ? C / 32 : 1;
+    cw.tc.NT = 256; cw.tc.n_tiles = Lpad / 256; cw.tc.img_rows = 16 * (C / 32) * Lpad;
+    cw.tc.total_rows = (long long)B * cw.tc.img_rows;
+    cp.w_img_stride = (long long)16 * C * Lpad;
+    CK(launch_conv(c, cp, cw, 2.0 * B * L * (double)L * C * 16));
+  }
+  c.put(kbuf);
+  c.put(rnorm);
+
+  // ---- softmax over keys -> P[b, n, 0..Lpad)
+  Buf pbuf = c.get((size_t)B * L * Lpad * c.esz());
+  CK(softmax_rows((const float*)sbuf.p, Lpad, pbuf.p, dt, Lpad, (long long)B * L, L, c.stream));
+  if (attn_out) {
+    // cam_1 returns [B, L(keys), hs, ws]: transpose of P
+    // (small, test-only path: done with the generic layout kernel, P viewed as NHWC with C = L keys)
+    if (dt == DT_F32) CK(nhwc_to_nchw(pbuf.p, dt, attn_out, B, L, L, Lpad, 0, c.stream));
+    else CK(nhwc_to_nchw(pbuf.p, dt, attn_out, B, L, L, Lpad, 0, c.stream));
+  }
+  c.put(sbuf);
+  c.put(colm);
+
+  // ---- values + fold-sum
+  const size_t velems = (size_t)4 * B * 4 * Lpad * C;
+  Buf vbuf = c.get(velems * (tc ? 2 : 4));
+  CK(cam_pack_v(f.p, dt, vbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, c.stream));
+  for (int pc = 0; pc < 4; ++pc) {
+    ConvParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.x = pbuf.p; cp.in_dt = dt; cp.N = B; cp.Hi = hs; cp.Wi = ws; cp.Ci = Lpad; cp.ldx = Lpad;
+    cp.Ho = h / 2; cp.Wo = w / 2; cp.stride = 1; cp.ntaps = 4;
+    for (int t = 0; t < 4; ++t) { cp.dy[t] = (int8_t)(-(t / 2)); cp.dx[t] = (int8_t)(-(t % 2)); }
+    cp.bias = nullptr; cp.Cout = C;
+    cp.y = out; cp.out_dt = dt; cp.Hout = h; cp.Wout = w; cp.ldo = out_ld; cp.choff = 0;
+    cp.osy = 2; cp.ooy = pc / 2; cp.osx = 2; cp.oox = pc % 2;
+    cp.epi = EPI_LINEAR; cp.scale = 1.0f; cp.colscale = nullptr;
+    ClassW cw;
+    cw.ntaps = 4;
+    cw.CoutP = C;
+    const size_t per_pc = (size_t)B * 4 * Lpad * C;
+    cw.w_direct = (float*)vbuf.p + (tc ? 0 : pc * per_pc);
+    cw.has_tc = tc && (C % 16 == 0);
+    cw.tc.data = (const uint16_t*)vbuf.p + (tc ? pc * per_pc : 0);
+    cw.tc.ntaps = 4; cw.tc.nchunks = Lpad / 32; cw.tc.kch = 2; cw.tc.NT = C; cw.tc.n_tiles = 1;
+    cw.tc.img_rows = 4 * (Lpad / 32) * C;
+    cw.tc.total_rows = (long long)B * cw.tc.img_rows;
+    cp.w_img_stride = (long long)4 * Lpad * C;
+    CK(launch_conv(c, cp, cw, 2.0 * B * (h / 2) * (w / 2) * (double)C * L * 4));
+  }
+  c.put(vbuf);
+  c.put(pbuf);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ networks
+static const std::initializer_list<const char*> kTrunk9 = {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5",
+                                                           "conv6", "conv7_atrous", "conv8_atrous", "conv9_atrous"};
+
+// MDGenerator.forward: x [B,3,H,W], guide [B,1,H,W] -> mask1 (soft, NCHW), optional x_stage1; also the
+// binarised mask plane (mask1 > 0.5) when mask_bin != nullptr.
+static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, float* mask1, float* x_stage1, float* mask_bin) {
+  const int dt = c.act_dt();
+  Buf in8 = c.get((size_t)c.B * H * W * 8 * c.esz());
+  CK(pack8(x, guide, nullptr, in8.p, dt, c.B, H, W, PACK_IMG_ONE, 1.0f, 0, c.stream));
+  View x9;
+  Buf b9;
+  int rc = run_chain(c, 'M', with_prefix("", kTrunk9), View{in8.p, H, W, 8, 8}, true, in8, &x9, &b9);
+  if (rc) return rc;
+  if (x_stage1) {
+    // image decoder consumes the conv9 output (editline2_g.py:76-77)
+    View v16;
+    Buf b16;
+    rc = run_chain(c, 'M', with_prefix("conv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}), x9, false, Buf(), &v16, &b16);
+    if (rc) return rc;
+    rc = run_head(c, 'M', "conv17", v16, HEAD_TANH, nullptr, nullptr, nullptr, x_stage1, nullptr, nullptr);
+    if (rc) return rc;
+    c.put(b16);
+  }
+  View v;
+  Buf b;
+  rc = run_chain(c, 'M', with_prefix("", {"conv10_atrous", "conv_mask_11", "conv_mask_12", "conv_mask_13_upsample_conv", "conv_mask_14",
+                                          "conv_mask_15_upsample_conv", "conv_mask_16"}),
+                 x9, true, b9, &v, &b);
+  if (rc) return rc;
+  Buf scratch;
+  float* mb = mask_bin;
+  if (!mb) { scratch = c.get((size_t)c.B * H * W * 4); mb = (float*)scratch.p; }
+  rc = run_head(c, 'M', "conv_mask_17", v, HEAD_MASK, nullptr, nullptr, nullptr, mask1, mb, nullptr);
+  if (rc) return rc;
+  c.put(scratch);
+  c.put(b);
+  return 0;
+}
+
+// DeepFillC2Generator.forward. x, x2 [B,3,H,W]; mask, mask2 planes [B,H,W]; guide [B,H,W] or null (ones).
+// Outputs: x_stage1 (optional), x_stage2 (optional NCHW), composed (optional: fine*soft + img*(1-soft)).
+static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, const float* mask2, const float* guide, int H, int W,
+                    float* x_stage1, float* x_stage2, float* composed, const float* mask_soft, const float* blend_img) {
+  const int dt = c.act_dt();
+  const int* opt = c.m->opt;
+  const int h = H / 4, w = W / 4;
+  SE_REQUIRE(guide != nullptr, "guide=None (all-ones sketch) is not supported: pass the sketch tensor");
+  const size_t e = c.esz();
+
+  // ---- stage 1: coarse encoder + style ("warp-in") encoder -> 192-channel concat -> coarse decoder
+  Buf cat1 = c.get((size_t)c.B * h * w * 192 * e);
+  {
+    Buf in8 = c.get((size_t)c.B * H * W * 8 * e);
+    CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
+    std::vector<std::string> names = with_prefix("", kTrunk9);
+    names.push_back("conv10_atrous");
+    int rc = run_chain(c, 'G', names, View{in8.p, H, W, 8, 8}, true, in8, nullptr, nullptr, cat1.p, 192, 0);
+    if (rc) return rc;
+  }
+  {
+    Buf in8 = c.get((size_t)c.B * H * W * 8 * e);
+    CK(pack8(x2, guide, mask2, in8.p, dt, c.B, H, W, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M,
+             opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f, 1, c.stream));
+    std::vector<std::string> names = with_prefix("w", kTrunk9);
+    names.push_back("wconv10_atrous");
+    View v;
+    Buf b;
+    int rc = run_chain(c, 'G', names, View{in8.p, H, W, 8, 8}, true, in8, &v, &b);
+    if (rc) return rc;
+    Buf pooled = c.get((size_t)c.B * 96 * 4);
+    CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
+    CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, 192, 96, c.stream));
+    c.put(pooled);
+    c.put(b);
+  }
+  Buf xnow = c.get((size_t)c.B * H * W * 8 * e);
+  {
+    View v16;
+    Buf b16;
+    int rc = run_chain(c, 'G', with_prefix("conv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}),
+                       View{cat1.p, h, w, 192, 192}, true, cat1, &v16, &b16);
+    if (rc) return rc;
+    rc = run_head(c, 'G', "conv17", v16, HEAD_COARSE, x, mask, nullptr, x_stage1, nullptr, xnow.p);
+    if (rc) return rc;
+    c.put(b16);
+  }
+  // ---- stage 2: hallucination branch + patch-match branch -> concat -> joint decoder
+  Buf cat2 = c.get((size_t)c.B * h * w * 192 * e);
+  {
+    std::vector<std::string> names = with_prefix("x", kTrunk9);
+    names.push_back("xconv10_atrous");
+    int rc = run_chain(c, 'G', names, View{xnow.p, H, W, 8, 8}, false, Buf(), nullptr, nullptr, cat2.p, 192, 0);
+    if (rc) return rc;
+  }
+  {
+    View pm;
+    Buf pmb;
+    int rc = run_chain(c, 'G', with_prefix("pm", {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}),
+                       View{xnow.p, H, W, 8, 8}, true, xnow, &pm, &pmb);
+    if (rc) return rc;
+    if (opt[SE_OPT_USE_CAM]) {
+      Buf ms = c.get((size_t)c.B * h * w * 4);
+      CK(avgpool4(mask, (float*)ms.p, c.B, H, W, c.stream));
+      Buf camo = c.get((size_t)c.B * h * w * 96 * e);
+      rc = run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr);
+      if (rc) return rc;
+      c.put(ms);
+      c.put(pmb);
+      pm = View{camo.p, h, w, 96, 96};
+      pmb = camo;
+    }
+    rc = run_chain(c, 'G', with_prefix("pm", {"conv9", "conv10"}), pm, true, pmb, nullptr, nullptr, cat2.p, 192, 96);
+    if (rc) return rc;
+  }
+  {
+    View v16;
+    Buf b16;
+    int rc = run_chain(c, 'G', with_prefix("allconv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}),
+                       View{cat2.p, h, w, 192, 192}, true, cat2, &v16, &b16);
+    if (rc) return rc;
+    if (composed) {
+      rc = run_head(c, 'G', "allconv17", v16, HEAD_FINE, blend_img, nullptr, mask_soft, composed, x_stage2, nullptr);
+    } else {
+      rc = run_head(c, 'G', "allconv17", v16, HEAD_TANH, nullptr, nullptr, nullptr, x_stage2, nullptr, nullptr);
+    }
+    if (rc) return rc;
+    c.put(b16);
+  }
+  return 0;
+}
+
+// run `fn` twice: dry (arena peak) then for real
+template <typename F>
+static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn) {
+  SE_REQUIRE(m && m->finalized, "model not finalized");
+  SE_REQUIRE(prec >= 0 && prec <= 2, "precision");
+  Ctx c;
+  c.m = m; c.stream = stream; c.prec = prec; c.B = B;
+  c.dry = true;
+  c.arena.reset(nullptr);
+  int rc = fn(c);
+  if (rc) return rc;
+  const size_t need = c.arena.peak + 4096;
+  if (need > m->arena_bytes) {
+    SE_CUDA_OK(cudaStreamSynchronize(stream));
+    if (m->arena) SE_CUDA_OK(cudaFree(m->arena));
+    m->arena = nullptr;
+    m->arena_bytes = 0;
+    SE_CUDA_OK(cudaMalloc(&m->arena, need));
+    m->arena_bytes = need;
+  }
+  c.dry = false;
+  c.arena.reset((char*)m->arena);
+  g_launches = 0;
+  return fn(c);
+}
+
+static int check_hw(int H, int W) {
+  SE_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "H and W must be multiples of 8 and >= 16 (two stride-2 convs, 4x4 mask pool, stride-2 patch grid)");
+  return 0;
+}
+
+}  // namespace se
+
+// ============================================================================================ C ABI
+extern "C" {
+
+const char* se_last_error(void) { return se::last_error(); }
+int se_abi_version(void) { return 1; }
+
+int se_model_create(se_model** out) {
+  SE_REQUIRE(out != nullptr, "out");
+  se_model* m = new se_model();
+  for (char net : {'M', 'G'}) {
+    ArchTable t = make_arch(net);
+    for (size_t i = 0; i < t.specs.size(); ++i) {
+      Layer L;
+      L.spec = t.specs[i];
+      L.name = t.names[i];
+      m->layers[std::string(1, net) + "." + t.names[i]] = L;
+    }
+  }
+  *out = m;
+  return 0;
+}
+
+void se_model_destroy(se_model* m) {
+  if (!m) return;
+  for (void* p : m->owned) cudaFree(p);
+  if (m->arena) cudaFree(m->arena);
+  delete m;
+}
+
+int se_model_set_layer(se_model* m, char net, const char* layer, const float* weight, const float* bias, int cout, int cin, int ksize) {
+  SE_REQUIRE(m && layer && weight && bias, "null argument");
+  SE_REQUIRE(!m->finalized, "model already finalized");
+  Layer* L = find_layer(m, net, layer);
+  SE_REQUIRE(L != nullptr, std::string("no such layer: net") + net + "." + layer);
+  SE_REQUIRE(L->spec.cout == cout && L->spec.cin == cin && L->spec.k == ksize,
+             std::string("shape mismatch for ") + layer + ": expected [" + std::to_string(L->spec.cout) + "," + std::to_string(L->spec.cin) + "," +
+                 std::to_string(L->spec.k) + "," + std::to_string(L->spec.k) + "]");
+  L->w_host.assign(weight, weight + (size_t)cout * cin * ksize * ksize);
+  L->b_host.assign(bias, bias + cout);
+  L->set = true;
+  return 0;
+}
+
+int se_model_set_option(se_model* m, int option, int value) {
+  SE_REQUIRE(m && option >= 0 && option < 8, "option");
+  m->opt[option] = value;
+  return 0;
+}
+
+int se_model_finalize(se_model* m) {
+  SE_REQUIRE(m, "model");
+  SE_REQUIRE(!m->finalized, "model already finalized");
+  int ndev = 0;
+  SE_CUDA_OK(cudaGetDeviceCount(&ndev));
+  SE_REQUIRE(ndev > 0, "no CUDA device: sketchedit_b200 has no CPU fallback");
+  for (auto& kv : m->layers) {
+    SE_REQUIRE(kv.second.set, "layer not set: net" + kv.first);
+    int rc = pack_layer(m, kv.second);
+    if (rc) return rc;
+    kv.second.w_host.clear();
+    kv.second.w_host.shrink_to_fit();
+  }
+  m->finalized = true;
+  return 0;
+}
+
+int se_forward_inference(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision, float* composed,
+                         float* mask, float* coarse, float* fine, float* mask_image, const float* mask_bin_in, float* mask_bin_out,
+                         void* stream) {
+  SE_REQUIRE(image && sketch && composed && mask, "null tensor");
+  int rc = check_hw(H, W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_arena(m, precision, B, st, [&](Ctx& c) -> int {
+    Buf mb = c.get((size_t)B * H * W * 4);
+    int r = run_netM(c, image, sketch, H, W, mask, mask_image, (float*)mb.p);
+    if (r) return r;
+    const float* mbin = (const float*)mb.p;
+    if (mask_bin_in) mbin = mask_bin_in;
+    if (mask_bin_out && !c.dry) {
+      SE_CUDA_OK(cudaMemcpyAsync(mask_bin_out, mbin, (size_t)B * H * W * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    // generate_fake: netG(inputs, inputs, mask_bin, mask_bin, line)   (editline2_model.py:368)
+    r = run_netG(c, image, image, mbin, mbin, sketch, H, W, coarse, fine, composed, mask, image);
+    if (r) return r;
+    c.put(mb);
+    return 0;
+  });
+}
+
+int se_netM_forward(se_model* m, const float* x, const float* guide, int B, int H, int W, int precision, float* mask1, float* x_stage1,
+                    void* stream) {
+  SE_REQUIRE(x && guide && mask1, "null tensor");
+  int rc = check_hw(H, W);
+  if (rc) return rc;
+  return with_arena(m, precision, B, (cudaStream_t)stream, [&](Ctx& c) -> int { return run_netM(c, x, guide, H, W, mask1, x_stage1, nullptr); });
+}
+
+int se_netG_forward(se_model* m, const float* x, const float* x2, const float* mask, const float* mask2, const float* guide, int B, int H,
+                    int W, int precision, float* x_stage1, float* x_stage2, void* stream) {
+  SE_REQUIRE(x && x2 && mask && mask2 && x_stage2, "null tensor");
+  int rc = check_hw(H, W);
+  if (rc) return rc;
+  return with_arena(m, precision, B, (cudaStream_t)stream,
+                    [&](Ctx& c) -> int { return run_netG(c, x, x2, mask, mask2, guide, H, W, x_stage1, x_stage2, nullptr, nullptr, nullptr); });
+}
+
+int se_gated_conv_forward(se_model* m, char net, const char* layer, const float* x, int B, int H, int W, int precision, float* y,
+                          void* stream) {
+  SE_REQUIRE(m && layer && x && y, "null argument");
+  Layer* L = find_layer(m, net, layer);
+  SE_REQUIRE(L != nullptr, std::string("no such layer: ") + layer);
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_arena(m, precision, B, st, [&](Ctx& c) -> int {
+    const Spec& s = L->spec;
+    const int dt = c.act_dt();
+    const int Ci = L->is_head ? 12 : L->Ci;
+    Buf in = c.get((size_t)B * H * W * Ci * c.esz());
+    if (!c.dry && Ci != s.cin) SE_CUDA_OK(cudaMemsetAsync(in.p, 0, in.bytes, st));
+    CK(nchw_to_nhwc(x, in.p, dt, B, s.cin, H * W, Ci, 0, st));
+    int Ho, Wo;
+    out_dims(s, H, W, &Ho, &Wo);
+    if (L->is_head) {
+      // raw conv (activation=None / cout==3, utils.py:27): run through the direct kernel, fp32 out
+      Buf o = c.get((size_t)B * Ho * Wo * s.cout * 4);
+      ConvParams cp;
+      memset(&cp, 0, sizeof(cp));
+      ClassW& cw = L->cls[0];
+      cp.x = in.p; cp.in_dt = dt; cp.N = B; cp.Hi = H; cp.Wi = W; cp.Ci = Ci; cp.ldx = Ci;
+      cp.Ho = Ho; cp.Wo = Wo; cp.stride = 1; cp.ntaps = cw.ntaps;
+      memcpy(cp.dy, cw.dy, sizeof(cp.dy));
+      memcpy(cp.dx, cw.dx, sizeof(cp.dx));
+      cp.w = cw.w_direct; cp.bias = L->bias; cp.Cout = s.cout;
+      cp.y = o.p; cp.out_dt = DT_F32; cp.Hout = Ho; cp.Wout = Wo; cp.ldo = s.cout; cp.choff = 0;
+      cp.osy = cp.osx = 1; cp.epi = EPI_LINEAR; cp.scale = 1.0f;
+      CK(direct_launch(cp, cw.CoutP, precision == SE_PREC_FP32_EXACT, st));
+      CK(nhwc_to_nchw(o.p, DT_F32, y, B, s.cout, Ho * Wo, s.cout, 0, st));
+      c.put(o);
+    } else {
+      const int cg = s.cout / 2;
+      Buf o = c.get((size_t)B * Ho * Wo * cg * c.esz());
+      int r = run_layer(c, *L, View{in.p, H, W, Ci, Ci}, o.p, cg, 0);
+      if (r) return r;
+      CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, st));
+      c.put(o);
+    }
+    c.put(in);
+    return 0;
+  });
+}
+
+int se_contextual_attention_forward(const float* feat, const float* mask_s, int B, int C, int h, int w, int precision, float* out,
+                                    float* attn, void* stream) {
+  SE_REQUIRE(feat && mask_s && out, "null tensor");
+  static se_model* holder = nullptr;   // arena owner for the model-less operator call
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!holder) { holder = new se_model(); holder->finalized = true; }
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_arena(holder, precision, B, st, [&](Ctx& c) -> int {
+    const int dt = c.act_dt();
+    Buf in = c.get((size_t)B * h * w * C * c.esz());
+    CK(nchw_to_nhwc(feat, in.p, dt, B, C, h * w, C, 0, st));
+    Buf o = c.get((size_t)B * h * w * C * c.esz());
+    int r = run_cam(c, View{in.p, h, w, C, C}, mask_s, o.p, C, attn);
+    if (r) return r;
+    CK(nhwc_to_nchw(o.p, dt, out, B, C, h * w, C, 0, st));
+    c.put(o);
+    c.put(in);
+    return 0;
+  });
+}
+
+int se_outputs_to_uint8(const float* composed, const float* mask, int B, int H, int W, unsigned char* bgr_hwc, unsigned char* mask_u8,
+                        void* stream) {
+  SE_REQUIRE(composed && bgr_hwc && (mask || !mask_u8), "null tensor");
+  return to_uint8(composed, mask, bgr_hwc, mask_u8, B, H, W, (cudaStream_t)stream);
+}
+
+int se_last_launch_count(void) { return se::g_launches; }
+long long se_workspace_bytes(se_model* m) { return m ? (long long)m->arena_bytes : 0; }
+
+int se_tc_timing_enable(int on) {
+  g_tc_timing = on != 0;
+  g_ev_used = 0;
+  g_tc_flops = 0.0;
+  return 0;
+}
+
+int se_tc_time_ms(double* ms, int* launches, double* flops) {
+  double total = 0.0;
+  for (size_t i = 0; i < g_ev_used; ++i) {
+    float t = 0.0f;
+    SE_CUDA_OK(cudaEventSynchronize(g_ev_pool[i].second));
+    SE_CUDA_OK(cudaEventElapsedTime(&t, g_ev_pool[i].first, g_ev_pool[i].second));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = (int)g_ev_used;
+  if (flops) *flops = g_tc_flops;
+  g_ev_used = 0;
+  g_tc_flops = 0.0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,440 @@
+// Glue kernels of the generator forward: input packing, heads (12->3 / 12->1 conv + tanh/sigmoid +
+// blends), global pooling, mask pooling, contextual-attention operand packing and softmax, layout
+// conversion. All activations are NHWC; T is the activation storage type (bf16 fast path / fp32 exact).
+#include "se_common.cuh"
+#include "se_misc.h"
+
+namespace se {
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+#define SE_DISPATCH_T(dt, ...)                          \
+  if ((dt) == DT_F32) { using T = float; __VA_ARGS__; } \
+  else { using T = __nv_bfloat16; __VA_ARGS__; }
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------ pack8
+// reference editline2_g.py:62 (cat[image, sketch]) and editline_g.py:120-135 (mask-mul + cat).
+template <typename T>
+__global__ void pack8_kernel(const float* __restrict__ img, const float* __restrict__ sketch, const float* __restrict__ mask,
+                             T* __restrict__ out, int B, int H, int W, int img_mode, float sketch_scale, int write_mask) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W;
+  if (i >= B * HW) return;
+  const long long b = i / HW, pix = i % HW;
+  const float m = mask ? mask[i] : 0.0f;
+  const float a = img_mode == PACK_IMG_ONE ? 1.0f : (img_mode == PACK_IMG_ONE_MINUS_M ? 1.0f - m : m);
+  T v[8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = from_f<T>(img[(b * 3 + c) * HW + pix] * a);
+  v[3] = from_f<T>(sketch ? sketch[i] * sketch_scale : 0.0f);
+  v[4] = from_f<T>(write_mask ? m : 0.0f);
+  v[5] = v[6] = v[7] = from_f<T>(0.0f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) out[i * 8 + c] = v[c];
+}
+
+int pack8(const float* img, const float* sketch, const float* mask, void* out, int dt, int B, int H, int W, int img_mode,
+          float sketch_scale, int write_mask, cudaStream_t s) {
+  const long long n = (long long)B * H * W;
+  SE_DISPATCH_T(dt, (pack8_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(img, sketch, mask, (T*)out, B, H, W, img_mode, sketch_scale, write_mask)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ heads
+// 3x3 / pad 1 conv over a 12-channel NHWC map to COUT in {1,3} channels (reference conv17 /
+// conv_mask_17 / allconv17: raw conv, utils.py:27) fused with the caller-side nonlinearity:
+//   HEAD_MASK   sigmoid -> soft mask (NCHW) + binarised mask plane   (editline2_g.py:93, editline2_model.py:347)
+//   HEAD_TANH   tanh -> NCHW                                         (editline2_g.py:84)
+//   HEAD_COARSE tanh -> [optional NCHW], xnow = t*m + img*(1-m)*(1-m) packed to 8 ch   (editline_g.py:176-181)
+//   HEAD_FINE   tanh -> [optional NCHW], composed = t*soft + img*(1-soft) (NCHW)       (editline_g.py:220, editline2_model.py:132)
+template <typename T, int COUT>
+__global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w /*[9][12][COUT]*/, const float* __restrict__ bias,
+                            int B, int H, int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
+                            const float* __restrict__ mask_soft, float* __restrict__ out_nchw, float* __restrict__ out2,
+                            T* __restrict__ out_pack8, int no_mask_coarse) {
+  __shared__ float ws[9 * 12 * COUT + COUT];
+  for (int i = threadIdx.x; i < 9 * 12 * COUT; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < COUT) ws[9 * 12 * COUT + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W;
+  if (i >= B * HW) return;
+  const long long b = i / HW, pix = i % HW;
+  const int yy = (int)(pix / W), xx = (int)(pix % W);
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = ws[9 * 12 * COUT + o];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const T* xp = x + ((b * H + iy) * W + ix) * 12;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+      const float xv = to_f<T>(xp[c]);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[o] = fmaf(xv, ws[(t * 12 + c) * COUT + o], acc[o]);
+    }
+  }
+  if (mode == HEAD_MASK) {
+    const float s = 1.0f / (1.0f + expf(-acc[0]));
+    out_nchw[i] = s;
+    out2[i] = s > 0.5f ? 1.0f : 0.0f;
+    return;
+  }
+  float t3[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) t3[o] = tanhf(acc[o]);
+  if (mode == HEAD_TANH) {
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+  } else if (mode == HEAD_COARSE) {
+    const float m = mask_bin[i];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      if (out_nchw) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+      const float xin = img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      const float v = no_mask_coarse ? t3[o] : (t3[o] * m + xin * (1.0f - m));
+      out_pack8[i * 8 + o] = from_f<T>(v);
+    }
+#pragma unroll
+    for (int o = COUT; o < 8; ++o) out_pack8[i * 8 + o] = from_f<T>(0.0f);
+  } else {  // HEAD_FINE
+    const float m = mask_soft[i];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      if (out2) out2[(b * COUT + o) * HW + pix] = t3[o];
+      out_nchw[(b * COUT + o) * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+    }
+  }
+}
+
+int head(const void* x, int dt, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
+         const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
+         cudaStream_t s) {
+  const long long n = (long long)B * H * W;
+  SE_REQUIRE(cout == 1 || cout == 3, "head cout");
+  SE_DISPATCH_T(dt, {
+    if (cout == 1)
+      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse);
+    else
+      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse);
+  });
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ plane reductions
+// per (image, channel) reduction over the h x w plane of an NHWC map:
+//   RED_MAX / RED_AVG      global pooling            (editline_g.py:160-165)
+//   RED_RNORM              1/sqrt(sum x^2 + 1e-8)    (splitcam.py:40)
+template <typename T>
+__global__ void plane_reduce_kernel(const T* __restrict__ x, int ldx, int C, int HW, int mode, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = (mode == RED_MAX) ? -INFINITY : 0.0f;
+  if (c < C) {
+    const T* xp = x + (size_t)b * HW * ldx + c;
+    for (int p = threadIdx.y; p < HW; p += 8) {
+      const float v = to_f<T>(xp[(size_t)p * ldx]);
+      if (mode == RED_MAX) acc = fmaxf(acc, v);
+      else if (mode == RED_AVG) acc += v;
+      else acc = fmaf(v, v, acc);
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) {
+      const float v = red[j][threadIdx.x];
+      acc = (mode == RED_MAX) ? fmaxf(acc, v) : acc + v;
+    }
+    if (mode == RED_AVG) acc /= (float)HW;
+    if (mode == RED_RNORM) acc = 1.0f / sqrtf(acc + 1e-8f);
+    out[(size_t)b * C + c] = acc;
+  }
+}
+
+int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int mode, float* out, cudaStream_t s) {
+  dim3 grid(cdiv(C, 32), B), block(32, 8);
+  SE_DISPATCH_T(dt, (plane_reduce_kernel<T><<<grid, block, 0, s>>>((const T*)x, ldx, C, HW, mode, out)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// nearest 1x1 -> h x w broadcast of the pooled vector into channels [choff, choff+C) of an NHWC map
+// (editline_g.py:166-167: interpolate + cat).
+template <typename T>
+__global__ void broadcast_kernel(const float* __restrict__ v, T* __restrict__ y, int C, int HW, int ldo, int choff, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const long long b = pix / HW;
+  y[pix * ldo + choff + c] = from_f<T>(v[b * C + c]);
+}
+
+int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, cudaStream_t s) {
+  const long long total = (long long)B * HW * C;
+  SE_DISPATCH_T(dt, (broadcast_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(v, (T*)y, C, HW, ldo, choff, total)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ mask pooling
+// avg_pool2d(mask, 4, 4) (editline_g.py:204) and the per-key valid flag of cam_1
+// (splitcam.py:49-53,89-90: mean over the 4x4 patch of (1 - mask_s) > th).
+__global__ void avgpool4_kernel(const float* __restrict__ m, float* __restrict__ out, int B, int H, int W) {
+  const int h = H / 4, w = W / 4;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * h * w) return;
+  const int x = (int)(i % w), y = (int)((i / w) % h);
+  const long long b = i / ((long long)h * w);
+  float a = 0.0f;
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v) a += m[(b * H + 4 * y + u) * W + 4 * x + v];
+  out[i] = a * (1.0f / 16.0f);
+}
+
+int avgpool4(const float* m, float* out, int B, int H, int W, cudaStream_t s) {
+  avgpool4_kernel<<<cdiv((long long)B * (H / 4) * (W / 4), 256), 256, 0, s>>>(m, out, B, H, W);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void cam_colmask_kernel(const float* __restrict__ mask_s, float* __restrict__ out, int B, int h, int w, int hs, int ws,
+                                   int patch, int stride, float th) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * hs * ws) return;
+  const int lx = (int)(i % ws), ly = (int)((i / ws) % hs);
+  const long long b = i / ((long long)hs * ws);
+  float a = 0.0f;
+  for (int u = 0; u < patch; ++u)
+    for (int v = 0; v < patch; ++v) a += 1.0f - mask_s[(b * h + ly * stride + u) * w + lx * stride + v];
+  // the reference takes mean over v then over u of exact multiples of 1/16: the order does not matter
+  out[i] = (a / (float)(patch * patch) > th) ? 1.0f : 0.0f;
+}
+
+int cam_colmask(const float* mask_s, float* out, int B, int h, int w, int hs, int ws, float th, cudaStream_t s) {
+  cam_colmask_kernel<<<cdiv((long long)B * hs * ws, 256), 256, 0, s>>>(mask_s, out, B, h, w, hs, ws, 4, 2, th);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ attention operands
+// Keys  K[l][(u,v,c)] = f[2ly+u, 2lx+v, c] * rnorm[c]        (splitcam.py:39-44, norm_type 1, 4x4 / stride 2)
+// tcgen05 layout: bf16 [b][tap=(u*4+v)][chunk=c/32][Lpad rows][32]
+template <typename T>
+__global__ void cam_pack_k_tc_kernel(const T* __restrict__ f, const float* __restrict__ rnorm, __nv_bfloat16* __restrict__ out,
+                                     int B, int h, int w, int C, int ws, int L, int Lpad, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % 32);
+  long long r = i / 32;
+  const int l = (int)(r % Lpad); r /= Lpad;
+  const int nch = C / 32;
+  const int chunk = (int)(r % nch); r /= nch;
+  const int tap = (int)(r % 16);
+  const long long b = r / 16;
+  float v = 0.0f;
+  if (l < L) {
+    const int ly = l / ws, lx = l % ws, u = tap / 4, vv = tap % 4, c = chunk * 32 + k;
+    v = to_f<T>(f[((b * h + 2 * ly + u) * w + 2 * lx + vv) * C + c]) * rnorm[b * C + c];
+  }
+  out[i] = __float2bfloat16(v);
+}
+
+// direct layout: fp32 [b][tap][c][CoutP]
+template <typename T>
+__global__ void cam_pack_k_direct_kernel(const T* __restrict__ f, const float* __restrict__ rnorm, float* __restrict__ out,
+                                         int B, int h, int w, int C, int ws, int L, int CoutP, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int l = (int)(i % CoutP);
+  long long r = i / CoutP;
+  const int c = (int)(r % C); r /= C;
+  const int tap = (int)(r % 16);
+  const long long b = r / 16;
+  float v = 0.0f;
+  if (l < L) {
+    const int ly = l / ws, lx = l % ws, u = tap / 4, vv = tap % 4;
+    v = to_f<T>(f[((b * h + 2 * ly + u) * w + 2 * lx + vv) * C + c]) * rnorm[b * C + c];
+  }
+  out[i] = v;
+}
+
+int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L,
+               int Lpad, cudaStream_t s) {
+  const long long total = (long long)B * 16 * C * Lpad;
+  if (tc_layout) {
+    SE_REQUIRE(C % 32 == 0, "C % 32");
+    SE_DISPATCH_T(dt, (cam_pack_k_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (__nv_bfloat16*)out, B, h, w, C, ws, L, Lpad, total)));
+  } else {
+    SE_DISPATCH_T(dt, (cam_pack_k_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (float*)out, B, h, w, C, ws, L, Lpad, total)));
+  }
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Values for the fold-sum written as 4 sub-pixel (parity) 2x2 "convolutions" over the token image
+// P[b, ny, nx, l] (splitcam.py:152, utils.py:102-128):
+//   out[2yy+py, 2xx+px, c] = sum_{a,b in {0,1}} sum_l P[yy-a, xx-b, l] * f[2ly+py+2a, 2lx+px+2b, c]
+// tcgen05 layout: bf16 [pc][b][tap=(a*2+b)][chunk=l/32][C rows][32]
+template <typename T>
+__global__ void cam_pack_v_tc_kernel(const T* __restrict__ f, __nv_bfloat16* __restrict__ out, int B, int h, int w, int C, int ws,
+                                     int L, int Lpad, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % 32);
+  long long r = i / 32;
+  const int c = (int)(r % C); r /= C;
+  const int nch = Lpad / 32;
+  const int chunk = (int)(r % nch); r /= nch;
+  const int tap = (int)(r % 4); r /= 4;
+  const long long b = r % B;
+  const int pc = (int)(r / B);
+  const int l = chunk * 32 + k;
+  float v = 0.0f;
+  if (l < L) {
+    const int ly = l / ws, lx = l % ws, py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
+    v = to_f<T>(f[((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + c]);
+  }
+  out[i] = __float2bfloat16(v);
+}
+
+// direct layout: fp32 [pc][b][tap][l (Ci = Lpad)][CoutP = C]
+template <typename T>
+__global__ void cam_pack_v_direct_kernel(const T* __restrict__ f, float* __restrict__ out, int B, int h, int w, int C, int ws, int L,
+                                         int Lpad, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  long long r = i / C;
+  const int l = (int)(r % Lpad); r /= Lpad;
+  const int tap = (int)(r % 4); r /= 4;
+  const long long b = r % B;
+  const int pc = (int)(r / B);
+  float v = 0.0f;
+  if (l < L) {
+    const int ly = l / ws, lx = l % ws, py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
+    v = to_f<T>(f[((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + c]);
+  }
+  out[i] = v;
+}
+
+int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L, int Lpad, cudaStream_t s) {
+  const long long total = 4LL * B * 4 * Lpad * C;
+  if (tc_layout) {
+    SE_REQUIRE(Lpad % 32 == 0, "Lpad % 32");
+    SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (__nv_bfloat16*)out, B, h, w, C, ws, L, Lpad, total)));
+  } else {
+    SE_DISPATCH_T(dt, (cam_pack_v_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (float*)out, B, h, w, C, ws, L, Lpad, total)));
+  }
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// softmax over the key axis of the logits S[row][0..L) (fp32, row pitch lds) -> P[row][0..Lpad) with
+// zero padding (splitcam.py:105; the scale 10 and the key mask are already applied by the GEMM epilogue).
+template <typename T>
+__global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, T* __restrict__ P, int ldp, int L) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const float* s = S + row * lds;
+  T* p = P + row * ldp;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, s[i]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) sum += expf(s[i] - mx);
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.0f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < ldp; i += blockDim.x) p[i] = from_f<T>(i < L ? expf(s[i] - mx) * inv : 0.0f);
+}
+
+int softmax_rows(const float* S, int lds, void* P, int dt, int ldp, long long rows, int L, cudaStream_t s) {
+  SE_DISPATCH_T(dt, (softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, s>>>(S, lds, (T*)P, ldp, L)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ layout conversion
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int C, int HW, int ldo, int choff, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const long long b = pix / HW, p = pix % HW;
+  y[pix * ldo + choff + c] = from_f<T>(x[(b * C + c) * HW + p]);
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int C, int HW, int ldx, int choff, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i % HW;
+  const long long r = i / HW;
+  const int c = (int)(r % C);
+  const long long b = r / C;
+  y[i] = to_f<T>(x[(b * HW + p) * ldx + choff + c]);
+}
+
+int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s) {
+  const long long total = (long long)B * C * HW;
+  SE_DISPATCH_T(dt, (nchw_to_nhwc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, (T*)y, C, HW, ldo, choff, total)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int nhwc_to_nchw(const void* x, int dt, float* y, int B, int C, int HW, int ldx, int choff, cudaStream_t s) {
+  const long long total = (long long)B * C * HW;
+  SE_DISPATCH_T(dt, (nhwc_to_nchw_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)x, y, C, HW, ldx, choff, total)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// test.py:25-27,33-35: (mask*255).astype(uint8); ((x+1)/2*255).astype(uint8) (truncation), CHW->HWC, RGB->BGR
+__global__ void to_uint8_kernel(const float* __restrict__ comp, const float* __restrict__ mask, unsigned char* __restrict__ bgr,
+                                unsigned char* __restrict__ mk, int B, long long HW) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const long long b = i / HW, pix = i % HW;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = (comp[(b * 3 + c) * HW + pix] + 1.0f) / 2.0f * 255.0f;
+    bgr[i * 3 + (2 - c)] = (unsigned char)(int)v;
+  }
+  if (mk) mk[i] = (unsigned char)(int)(mask[i] * 255.0f);
+}
+
+int to_uint8(const float* comp, const float* mask, unsigned char* bgr, unsigned char* mk, int B, int H, int W, cudaStream_t s) {
+  const long long HW = (long long)H * W;
+  to_uint8_kernel<<<cdiv(B * HW, 256), 256, 0, s>>>(comp, mask, bgr, mk, B, HW);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// zero-fill helper for padded channel tails
+int fill_zero(void* p, size_t bytes, cudaStream_t s) {
+  SE_CUDA_OK(cudaMemsetAsync(p, 0, bytes, s));
+  return 0;
+}
+
+}  // namespace se
