@@ -1,0 +1,52 @@
+"""List-file test dataset (reference data/testimage_dataset.py:13-111): each line of ``--image_lists`` names
+an image under ``--image_dirs`` and a sketch under ``--mask_dirs``. The image becomes a [-1,1] RGB tensor,
+the sketch an 'L' image resized to the image size and binarised with ``> 0``. Several ';'-separated
+dir/list triples may be given."""
+import os
+
+import numpy as np
+import torch
+import torch.utils.data
+from PIL import Image
+
+
+class TestImageDataset(torch.utils.data.Dataset):
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        parser.add_argument("--image_dirs", type=str, required=False, default="./datasets/face_release/images")
+        parser.add_argument("--mask_dirs", type=str, required=False, default="./datasets/face_release/edges")
+        parser.add_argument("--image_lists", type=str, required=False, default="./datasets/face_release/list.txt")
+        parser.add_argument("--image_postfix", type=str, default=".png")
+        parser.add_argument("--mask_postfix", type=str, default=".png")
+        parser.add_argument("--output_labels", type=str, required=False, help="';'-separated prefixes for output names")
+        parser.add_argument("--output_dir", type=str, required=False, default="./results")
+        parser.add_argument("--output_mask_dir", type=str, required=False)
+        return parser
+
+    def initialize(self, opt):
+        self.opt = opt
+        os.makedirs(opt.output_dir, exist_ok=True)
+        if opt.output_mask_dir is not None:
+            os.makedirs(opt.output_mask_dir, exist_ok=True)
+        labels = opt.output_labels.split(";") if opt.output_labels else None
+        self.items = []
+        for i, (idir, mdir, lst) in enumerate(zip(opt.image_dirs.split(";"), opt.mask_dirs.split(";"),
+                                                  opt.image_lists.split(";"))):
+            with open(lst) as f:
+                stems = [ln.strip("\n").replace(opt.image_postfix, "") for ln in f if ln.strip()]
+            for s in stems:
+                out = (labels[i] + "_" if labels else "") + s + opt.image_postfix
+                self.items.append((os.path.join(idir, s + opt.image_postfix), os.path.join(mdir, s + opt.mask_postfix), out))
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, index):
+        ipath, mpath, out = self.items[index]
+        img = Image.open(ipath).convert("RGB")
+        w, h = img.size
+        image = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div(255)
+        image = (image - 0.5) / 0.5                                   # ToTensor + Normalize(0.5, 0.5)
+        sk = Image.open(mpath).convert("L").resize((w, h))
+        sketch = (torch.from_numpy(np.asarray(sk, dtype=np.uint8).copy()).float().div(255)[None] > 0).float()
+        return {"image": image, "gt": image, "mask": sketch, "path": out}

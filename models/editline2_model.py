@@ -1,0 +1,76 @@
+"""EditLine2Model, inference subset (reference models/editline2_model.py:49-147, 184-242, 338-370).
+
+``forward(data, mode)`` with mode 'inference' returns ``(composed_image, mask)`` exactly like the
+reference: netM predicts the edit mask from (image, sketch), the mask is binarised at 0.5, netG inpaints,
+and the result is blended with the SOFT mask. All of it is one C-ABI call (``se_forward_inference``) on the
+B200 kernels; tensors in ``data`` may live on the CPU (they are copied to the GPU like the reference's
+``preprocess_input`` does) and the outputs are CUDA tensors. Training modes are out of scope."""
+import torch
+
+import models.networks as networks
+import util.util as util
+
+
+class EditLine2Model(torch.nn.Module):
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        networks.modify_commandline_options(parser, is_train)
+        parser.add_argument("--precision", default="bf16", choices=("bf16", "fp32"),
+                            help="B200 arithmetic: bf16 tensor-core path or fp32 CUDA-core parity path")
+        return parser
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        if getattr(opt, "isTrain", False):
+            raise NotImplementedError("only the inference path is implemented on B200")
+        self.precision = getattr(opt, "precision", "bf16")
+        self.netM, self.netG, self.netD = self.initialize_networks(opt)
+        self._engine = None
+        self._engine_key = None
+
+    def use_gpu(self):
+        return len(self.opt.gpu_ids) > 0
+
+    def initialize_networks(self, opt):
+        netG = networks.define_G(opt)
+        saved = opt.netG
+        opt.netG = "MD"
+        netM = networks.define_G(opt)
+        opt.netG = saved
+        if not hasattr(opt, "isSkip"):           # same escape hatch as the reference (:195)
+            netG = util.load_network(netG, "G", opt.which_epoch, opt)
+            netM = util.load_network(netM, "M", opt.which_epoch, opt)
+        return netM, netG, None
+
+    def engine(self):
+        from sketchedit_b200.engine import Engine
+        key = self.netM._weights_key() + self.netG._weights_key()
+        if self._engine is None or key != self._engine_key:
+            eng = Engine()
+            eng.load_state_dict("M", self.netM.state_dict())
+            eng.load_state_dict("G", self.netG.state_dict())
+            self.netG._configure_engine(eng)
+            eng.finalize()
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    def preprocess_input(self, data):
+        dev = torch.device("cuda")
+        image = data["image"].to(dev, torch.float32, non_blocking=True)
+        line = data["mask"].to(dev, torch.float32, non_blocking=True)
+        return image, line
+
+    def forward(self, data, mode, is_real_im=True):
+        image, line = self.preprocess_input(data)
+        if mode == "inference":
+            composed, mask, _ = self.engine().inference(image, line, precision=self.precision)
+            return composed, mask
+        if mode == "visualize":
+            composed, mask, ex = self.engine().inference(image, line, precision=self.precision,
+                                                         want=("coarse", "fine", "mask_image", "mask_bin"))
+            mb = ex["mask_bin"]
+            visline = image * (1 - line) + torch.ones_like(image) * line
+            return {"mask": mask, "maskim": ex["mask_image"], "visline": visline, "coarse": ex["coarse"],
+                    "composed": ex["fine"] * mb + image * (1 - mb), "gt": data.get("gt", data["image"])}
+        raise ValueError("|mode| is invalid or training-only: %r" % (mode,))

@@ -353,6 +353,15 @@ static Layer* find_layer(se_model* m, char net, const std::string& name) {
   auto it = m->layers.find(std::string(1, net) + "." + name);
   return it == m->layers.end() ? nullptr : &it->second;
 }
+// layer that has weights (forward paths); nullptr + error text otherwise
+static Layer* find_ready(se_model* m, char net, const std::string& name) {
+  Layer* L = find_layer(m, net, name);
+  if (L && !L->set) {
+    set_error(std::string("weights of net") + net + " were never loaded (layer " + name + ")");
+    return nullptr;
+  }
+  return L;
+}
 
 static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw, double flops) {
   if (c.prec == SE_PREC_BF16_TC && cw.has_tc) {
@@ -418,8 +427,8 @@ static int run_chain(Ctx& c, char net, const std::vector<std::string>& names, Vi
   Buf cur_buf = in_buf;
   bool cur_owned = free_in;
   for (size_t i = 0; i < names.size(); ++i) {
-    Layer* L = find_layer(c.m, net, names[i]);
-    SE_REQUIRE(L != nullptr, "unknown layer " + names[i]);
+    Layer* L = find_ready(c.m, net, names[i]);
+    SE_REQUIRE(L != nullptr, "unknown or unloaded layer " + names[i] + ": " + last_error());
     int Ho, Wo;
     out_dims(L->spec, cur.H, cur.W, &Ho, &Wo);
     const int cg = L->spec.cout / 2;
@@ -454,8 +463,8 @@ static std::vector<std::string> with_prefix(const std::string& pfx, std::initial
 
 static int run_head(Ctx& c, char net, const std::string& name, const View& in, int mode, const float* img, const float* mask_bin,
                     const float* mask_soft, float* out_nchw, float* out2, void* out_pack8) {
-  Layer* L = find_layer(c.m, net, name);
-  SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name);
+  Layer* L = find_ready(c.m, net, name);
+  SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name + ": " + last_error());
   CK(head(in.p, c.act_dt(), L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
           out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], c.stream));
   return 0;
@@ -774,8 +783,20 @@ int se_model_finalize(se_model* m) {
   int ndev = 0;
   SE_CUDA_OK(cudaGetDeviceCount(&ndev));
   SE_REQUIRE(ndev > 0, "no CUDA device: sketchedit_b200 has no CPU fallback");
+  // a net may be left out entirely (stand-alone netM / netG modules); a partially set net is an error
+  for (char net : {'M', 'G'}) {
+    int nset = 0, ntot = 0;
+    std::string first_missing;
+    for (auto& kv : m->layers)
+      if (kv.first[0] == net) {
+        ++ntot;
+        if (kv.second.set) ++nset;
+        else if (first_missing.empty()) first_missing = kv.first;
+      }
+    SE_REQUIRE(nset == 0 || nset == ntot, "layer not set: net" + first_missing);
+  }
   for (auto& kv : m->layers) {
-    SE_REQUIRE(kv.second.set, "layer not set: net" + kv.first);
+    if (!kv.second.set) continue;
     int rc = pack_layer(m, kv.second);
     if (rc) return rc;
     kv.second.w_host.clear();
@@ -829,8 +850,8 @@ int se_netG_forward(se_model* m, const float* x, const float* x2, const float* m
 int se_gated_conv_forward(se_model* m, char net, const char* layer, const float* x, int B, int H, int W, int precision, float* y,
                           void* stream) {
   SE_REQUIRE(m && layer && x && y, "null argument");
-  Layer* L = find_layer(m, net, layer);
-  SE_REQUIRE(L != nullptr, std::string("no such layer: ") + layer);
+  Layer* L = find_ready(m, net, layer);
+  SE_REQUIRE(L != nullptr, std::string("no such (loaded) layer: ") + layer);
   cudaStream_t st = (cudaStream_t)stream;
   return with_arena(m, precision, B, st, [&](Ctx& c) -> int {
     const Spec& s = L->spec;

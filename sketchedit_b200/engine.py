@@ -83,8 +83,10 @@ class Engine:
     @classmethod
     def from_state_dicts(cls, sd_M, sd_G, **options):
         e = cls()
-        e.load_state_dict("M", sd_M)
-        e.load_state_dict("G", sd_G)
+        if sd_M is not None:
+            e.load_state_dict("M", sd_M)
+        if sd_G is not None:
+            e.load_state_dict("G", sd_G)
         e.set_options(**options)
         e.finalize()
         return e

@@ -1,0 +1,36 @@
+"""Batch inference entry point -- same command line as the reference's test.py (reference test.py:12-37,
+test_celeb.sh, test_places.sh): build the dataloader and the model from the flags, run
+``model(data, mode='inference')`` per batch on the B200 kernels, convert to uint8 (truncating, like
+``astype(np.uint8)``), RGB->BGR, and write PNGs to --output_dir (masks to --output_mask_dir)."""
+import os
+
+import cv2
+import torch
+
+import data
+import models
+from options.test_options import TestOptions
+from sketchedit_b200.engine import outputs_to_uint8
+
+
+def main(argv=None):
+    opt = TestOptions().parse(argv)
+    dataloader = data.create_dataloader(opt)
+    model = models.create_model(opt)
+    model.eval()
+    for i, batch in enumerate(dataloader):
+        if i * opt.batchSize >= opt.how_many:
+            break
+        with torch.no_grad():
+            generated, mask = model(batch, mode="inference")
+        bgr, mk = outputs_to_uint8(generated, mask)       # device-side (x+1)/2*255 -> uint8 HWC BGR
+        bgr, mk = bgr.cpu().numpy(), mk.cpu().numpy()
+        for b, path in enumerate(batch["path"]):
+            print("process image... %s" % path)
+            assert cv2.imwrite(os.path.join(opt.output_dir, path), bgr[b])
+            if getattr(opt, "output_mask_dir", None) is not None:
+                assert cv2.imwrite(os.path.join(opt.output_mask_dir, path), mk[b])
+
+
+if __name__ == "__main__":
+    main()
