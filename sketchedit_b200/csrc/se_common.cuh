@@ -60,6 +60,7 @@ struct ConvParams {
   const void* x;        // NHWC, dtype in_dt, pixel pitch ldx elements
   int in_dt;
   int N, Hi, Wi, Ci, ldx;
+  long long x_row_pitch, x_img_pitch;   // elements; 0 = dense (Wi*ldx, Hi*Wi*ldx). ldx may be < Ci (overlapping windows)
   // position grid + taps
   int Ho, Wo, stride;
   int ntaps;
@@ -89,7 +90,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : (__expf(x) - 1.0f); }
 

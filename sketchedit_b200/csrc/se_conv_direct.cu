@@ -60,7 +60,9 @@ conv_direct_kernel(const ConvParams p, const int CoutP) {
   for (int t = 0; t < p.ntaps; ++t) {
     const int iy = py * p.stride + p.dy[t], ix = px * p.stride + p.dx[t];
     const bool inb = valid && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi;
-    const TIn* xp = xin + (((size_t)img * p.Hi + (inb ? iy : 0)) * p.Wi + (inb ? ix : 0)) * p.ldx;
+    const long long row_pitch = p.x_row_pitch ? p.x_row_pitch : (long long)p.Wi * p.ldx;
+    const long long img_pitch = p.x_img_pitch ? p.x_img_pitch : (long long)p.Hi * row_pitch;
+    const TIn* xp = xin + (size_t)img * img_pitch + (size_t)(inb ? iy : 0) * row_pitch + (size_t)(inb ? ix : 0) * p.ldx;
     for (int c0 = 0; c0 < p.Ci; c0 += DC_CK) {
       const int cc = min(DC_CK, p.Ci - c0);
       __syncthreads();

@@ -14,6 +14,10 @@
 #include "se_common.cuh"
 #include "se_conv_tc.h"
 
+#include <stdlib.h>
+
+#include <vector>
+
 namespace se {
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -83,9 +87,50 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// must be executed before the registers written by tmem_ld16 are read
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// write cnt (<= 16) consecutive channels of one pixel; static register indexing only (no local memory)
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* o, const float (&r)[16], int cnt, bool al8, bool al4) {
+  if (cnt == 16 && al8) {
+    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+    *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15]));
+  } else if (al4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * j + 4 <= cnt) *reinterpret_cast<uint2*>(o + 4 * j) = make_uint2(pack_bf16x2(r[4 * j], r[4 * j + 1]), pack_bf16x2(r[4 * j + 2], r[4 * j + 3]));
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i >= (cnt & ~3) && i < cnt) o[i] = __float2bfloat16(r[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cnt) o[i] = __float2bfloat16(r[i]);
+  }
+}
+__device__ __forceinline__ void store_row_f32(float* o, const float (&r)[16], int cnt, bool al4) {
+  if (cnt == 16 && al4) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cnt) o[i] = r[i];
+  }
 }
 
 // K-major, SWIZZLE_64B operand tile: rows of 64 B, 8-row atoms 512 B apart (cute::UMMA::SmemDescriptor).
@@ -152,14 +197,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.N * tiles_per_img * p.n_tiles;
-  const int groups = p.nchunks / p.kch;
-  const int ksteps = p.ntaps * groups;
+  const int total_q = p.ntaps * p.nchunks;   // flattened (tap, chunk) units; kch consecutive units per stage
+  const int ksteps = total_q / p.kch;
 
   if (warp == 0) {
     if (lane == 0) {
       // ================================================================== TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0, t_begin = clock64();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         int rest = tile / p.n_tiles;
@@ -169,22 +215,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = rest / p.tiles_y;
         const int x0 = tx * TILE_W * p.stride, y0 = ty * TILE_H * p.stride;
         const int wrow0 = img * p.w_img_rows + nt * p.NT;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int xs = x0 + p.dx[t], ys = y0 + p.dy[t];
-          for (int g = 0; g < groups; ++g) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-            uint8_t* sA = smem + (size_t)stage * stage_bytes;
-            uint8_t* sB = sA + p.kch * A_CHUNK_BYTES;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-            for (int j = 0; j < p.kch; ++j) {
-              const int chunk = g * p.kch + j;
-              tma_load_4d(sA + j * A_CHUNK_BYTES, &tmA, &full_bar[stage], chunk * KCHUNK, xs, ys, img);
-              tma_load_2d(sB + j * b_chunk_bytes, &tmB, &full_bar[stage], 0, wrow0 + (t * p.nchunks + chunk) * p.w_rows_tc);
-            }
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        for (int q0 = 0; q0 < total_q; q0 += p.kch) {
+          const long long tw = clock64();
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          t_wait += clock64() - tw;
+          uint8_t* sA = smem + (size_t)stage * stage_bytes;
+          uint8_t* sB = sA + p.kch * A_CHUNK_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          for (int j = 0; j < p.kch; ++j) {
+            const int q = q0 + j;
+            const int t = q / p.nchunks, chunk = q - t * p.nchunks;
+            tma_load_4d(sA + j * A_CHUNK_BYTES, &tmA, &full_bar[stage], chunk * KCHUNK, x0 + p.dx[t], y0 + p.dy[t], img);
+            tma_load_2d(sB + j * b_chunk_bytes, &tmB, &full_bar[stage], 0, wrow0 + q * p.w_rows_tc);
           }
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -194,14 +241,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
+      long long t_wfull = 0, t_wtmem = 0, t_begin = clock64();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
+        long long tw = clock64();
         mbar_wait(&tmem_empty[as], aphase ^ 1, 2);
+        t_wtmem += clock64() - tw;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
         for (int ks = 0; ks < ksteps; ++ks) {
+          tw = clock64();
           mbar_wait(&full_bar[stage], phase, 3);
+          t_wfull += clock64() - tw;
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sB = sA + p.kch * A_CHUNK_BYTES;
@@ -218,6 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
     }
   } else if (warp >= 4) {
     // ==================================================================== epilogue
@@ -225,6 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;             // tile row == TMEM lane == output position in tile
     const int ry = row / TILE_W, rx = row % TILE_W;
     int iter = 0;
+    long long t_wacc = 0, t_begin = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int nt = tile % p.n_tiles;
       int rest = tile / p.n_tiles;
@@ -234,7 +288,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int img = rest / p.tiles_y;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
+      const long long tw = clock64();
       mbar_wait(&tmem_full[as], aphase, 4);
+      t_wacc += clock64() - tw;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
       const int py = ty * TILE_H + ry, px = tx * TILE_W + rx;
@@ -244,65 +300,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if (p.epi == EPI_LINEAR) {
         const int n0 = nt * p.NT;
+        const float* cs = p.colscale ? p.colscale + (size_t)img * p.Cout : nullptr;
+        const bool al4 = ((p.ldo | p.choff) & 3) == 0, al8 = ((p.ldo | p.choff) & 7) == 0;
         for (int c0 = 0; c0 < p.NT; c0 += 16) {
-          if (n0 + c0 >= p.Cout) break;
+          const int cb = n0 + c0;
+          if (cb >= p.Cout) break;
           float v[16];
           tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
           if (valid) {
-            const int cnt = min(16, p.Cout - (n0 + c0));
-            const float* cs = p.colscale ? p.colscale + (size_t)img * p.Cout + n0 + c0 : nullptr;
+            const int cnt = min(16, p.Cout - cb);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float s = p.scale * ((cs && i < cnt) ? cs[i] : 1.0f);
-              v[i] = (v[i] + bias_s[n0 + c0 + i]) * s;
+              float sc = p.scale;
+              if (cs != nullptr && i < cnt) sc *= __ldg(cs + cb + i);
+              v[i] = (v[i] + bias_s[cb + i]) * sc;
             }
-            if (p.out_dt == DT_F32) {
-              float* o = reinterpret_cast<float*>(p.y) + opix * p.ldo + p.choff + n0 + c0;
-              if (cnt == 16) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              } else {
-                for (int i = 0; i < cnt; ++i) o[i] = v[i];
-              }
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.ldo + p.choff + n0 + c0;
-              if (cnt == 16) {
-                uint4 a = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                uint4 b = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-                *reinterpret_cast<uint4*>(o) = a;
-                *reinterpret_cast<uint4*>(o + 8) = b;
-              } else {
-                for (int i = 0; i < cnt; ++i) o[i] = __float2bfloat16(v[i]);
-              }
-            }
+            if (p.out_dt == DT_F32) store_row_f32(reinterpret_cast<float*>(p.y) + opix * p.ldo + p.choff + cb, v, cnt, al4);
+            else store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.ldo + p.choff + cb, v, cnt, al8, al4);
           }
         }
       } else {
         // gated: feature column c pairs with gate column c + half; both live in this thread's lane
         const int half = p.Cout >> 1;
+        const bool is_elu = (p.epi == EPI_GATE_ELU);
+        const bool al4 = ((p.ldo | p.choff) & 3) == 0, al8 = ((p.ldo | p.choff) & 7) == 0;
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.ldo + p.choff;
         for (int c0 = 0; c0 < half; c0 += 16) {
           float f[16], g[16];
           tmem_ld16(taddr + c0, f);
           tmem_ld16(taddr + half + c0, g);
+          tmem_ld_wait();
           if (valid) {
             const int cnt = min(16, half - c0);
-            float r[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = gate_act(f[i] + bias_s[c0 + i], g[i] + bias_s[half + c0 + i], p.epi);
-            if (cnt == 16) {
-              *reinterpret_cast<uint4*>(o + c0) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
-              *reinterpret_cast<uint4*>(o + c0 + 8) = make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15]));
-            } else {
-              for (int i = 0; i + 1 < cnt; i += 2) *reinterpret_cast<uint32_t*>(o + c0 + i) = pack_bf16x2(r[i], r[i + 1]);
-              if (cnt & 1) o[c0 + cnt - 1] = __float2bfloat16(r[cnt - 1]);
+            for (int i = 0; i < 16; ++i) {
+              const float fv = f[i] + bias_s[c0 + i], gv = g[i] + bias_s[half + c0 + i];
+              const float a = is_elu ? (fv > 0.0f ? fv : ex2_approx(fv * 1.4426950408889634f) - 1.0f) : fmaxf(fv, 0.0f);
+              f[i] = a * fmaf(0.5f, tanh_approx(0.5f * gv), 0.5f);     // a * sigmoid(g)
             }
+            store_row_bf16(o + c0, f, cnt, al8, al4);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
+    if (p.dbg && threadIdx.x == 128) { p.dbg[blockIdx.x * 8 + 5] = t_wacc; p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin; }
   }
 
   tc_fence_before();
@@ -334,6 +378,16 @@ static int g_smem_optin = 0;
 
 int tc_smem_budget() { return 200 * 1024; }
 
+// chunks per pipeline stage: the largest divisor of total_q whose stage stays under ~48 KB (SE_TC_STAGE_KB)
+int tc_choose_kch(int total_q, int NT) {
+  static int cap_kb = getenv("SE_TC_STAGE_KB") ? atoi(getenv("SE_TC_STAGE_KB")) : 48;
+  const int unit = A_CHUNK_BYTES + NT * KCHUNK * 2;
+  int best = 1;
+  for (int k = 1; k <= 8 && k <= total_q; ++k)
+    if (total_q % k == 0 && k * unit <= cap_kb * 1024) best = k;
+  return best;
+}
+
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes) {
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -342,7 +396,7 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   SE_REQUIRE((reinterpret_cast<uintptr_t>(c.x) & 15) == 0, "input base must be 16 B aligned");
   SE_REQUIRE(c.ntaps <= MAX_TAPS && c.ntaps == w.ntaps, "tap count mismatch");
   SE_REQUIRE(w.NT % 16 == 0 && w.NT >= 16 && w.NT <= 256, "NT");
-  SE_REQUIRE(w.nchunks % w.kch == 0, "kch must divide nchunks");
+  SE_REQUIRE((w.ntaps * w.nchunks) % w.kch == 0, "kch must divide ntaps*nchunks");
   SE_REQUIRE(w.nchunks * KCHUNK >= c.Ci, "weights do not cover Ci");
   SE_REQUIRE(c.stride >= 1 && c.stride <= 2, "stride");
   p.N = c.N; p.Ho = c.Ho; p.Wo = c.Wo;
@@ -393,7 +447,9 @@ int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
   {
     // activations: (C, W, H, N), box (32, 16*s, 8*s, 1) walked with element strides (1, s, s, 1)
     cuuint64_t dims[4] = {(cuuint64_t)c.Ci, (cuuint64_t)c.Wi, (cuuint64_t)c.Hi, (cuuint64_t)c.N};
-    cuuint64_t strides[3] = {(cuuint64_t)c.ldx * 2, (cuuint64_t)c.Wi * c.ldx * 2, (cuuint64_t)c.Hi * c.Wi * c.ldx * 2};
+    const long long row_pitch = c.x_row_pitch ? c.x_row_pitch : (long long)c.Wi * c.ldx;
+    const long long img_pitch = c.x_img_pitch ? c.x_img_pitch : (long long)c.Hi * row_pitch;
+    cuuint64_t strides[3] = {(cuuint64_t)c.ldx * 2, (cuuint64_t)row_pitch * 2, (cuuint64_t)img_pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)KCHUNK, (cuuint32_t)(TILE_W * c.stride), (cuuint32_t)(TILE_H * c.stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.x), dims, strides, box, estr,
@@ -413,8 +469,26 @@ int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
   }
   const int total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_tiles;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+  static const bool dbg_on = getenv("SE_TC_DEBUG") != nullptr;
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) SE_CUDA_OK(cudaMalloc(&dbg_buf, 8 * 8 * 1024));
+    SE_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 8 * 8 * 1024, stream));
+    p.dbg = dbg_buf;
+  }
   conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
   SE_CUDA_OK(cudaGetLastError());
+  if (dbg_on) {
+    SE_CUDA_OK(cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> h(8 * grid);
+    SE_CUDA_OK(cudaMemcpy(h.data(), dbg_buf, h.size() * 8, cudaMemcpyDeviceToHost));
+    double a[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 8 + k] / grid;
+    fprintf(stderr,
+            "[tc] N=%d %dx%d Ci=%d s=%d taps=%d NT=%d kch=%d stages=%d tiles=%d grid=%d | prod wait_empty %.0f/%.0f | mma wait_full %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f (cycles, mean per CTA)\n",
+            c.N, c.Ho, c.Wo, c.Ci, c.stride, c.ntaps, p.NT, p.kch, p.num_stages, total_tiles, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+  }
   return 0;
 }
 

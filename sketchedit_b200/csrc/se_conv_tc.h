@@ -11,7 +11,7 @@ struct TcWeights {
   const void* data = nullptr;   // device, bf16
   int ntaps = 0;
   int nchunks = 0;              // 32-channel chunks per tap (Cin padded with zeros)
-  int kch = 1;                  // chunks per pipeline stage
+  int kch = 1;                  // (tap,chunk) units per pipeline stage; divides ntaps*nchunks
   int NT = 0;                   // GEMM N per tile (Cout padded to 16), <= 256
   int n_tiles = 1;
   int img_rows = 0;             // rows per image for per-image weights (attention), 0 = shared
@@ -36,8 +36,10 @@ struct TcParams {
   int epi;
   float scale;
   const float* colscale;
+  unsigned long long* dbg;   // optional per-CTA role timers (SE_TC_DEBUG=1)
 };
 
+int tc_choose_kch(int total_q, int NT);
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes);
 int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream);
 

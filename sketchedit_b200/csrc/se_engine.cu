@@ -127,6 +127,7 @@ struct Layer {
   std::string name;
   int Ci = 0;                  // stored input channels (stems are packed to 8)
   bool is_head = false;
+  bool is_stem = false;
   bool set = false;
   std::vector<float> w_host, b_host;
   std::vector<ClassW> cls;
@@ -149,7 +150,11 @@ struct se_model {
 
 namespace se {
 
-static int stored_ci(const Spec& s) { return s.k == 5 ? 8 : s.cin; }
+// 5x5 stems read an 8-channel packed input through overlapping 4-pixel windows: 32 virtual channels
+// (pixel pitch 8 elements), see pack_layer / run_layer.
+constexpr int STEM_PADL = 2;                       // zero pixels left of the image in the packed buffer
+static inline int stem_wp(int W) { return W + 8; } // packed row length (2 left + 6 right zero pixels)
+static int stored_ci(const Spec& s) { return s.k == 5 ? 32 : s.cin; }
 
 static int upload(se_model* m, const void* host, size_t bytes, void** dev) {
   SE_CUDA_OK(cudaMalloc(dev, bytes));
@@ -167,7 +172,9 @@ static inline uint16_t f32_to_bf16_rn(float f) {
 }
 
 // effective tap = sum of source taps (ky,kx) of the OIHW kernel (deconv parity classes merge taps)
-struct EffTap { int dy, dx; std::vector<std::pair<int, int>> src; };
+// each source adds W[:, :, ky, kx] into the virtual input channels [ci_off, ci_off + cin)
+struct SrcTap { int ky, kx, ci_off; };
+struct EffTap { int dy, dx; std::vector<SrcTap> src; };
 
 static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, ClassW& cw) {
   const Spec& s = L.spec;
@@ -182,7 +189,7 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
     for (auto& sk : taps[t].src)
       for (int ci = 0; ci < s.cin; ++ci)
         for (int co = 0; co < Cout; ++co)
-          weff[((size_t)t * Ci + ci) * Cout + co] += L.w_host[(((size_t)co * s.cin + ci) * k + sk.first) * k + sk.second];
+          weff[((size_t)t * Ci + sk.ci_off + ci) * Cout + co] += L.w_host[(((size_t)co * s.cin + ci) * k + sk.ky) * k + sk.kx];
   }
   {
     std::vector<float> wd((size_t)cw.ntaps * Ci * cw.CoutP, 0.0f);
@@ -197,9 +204,8 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
     TcWeights& tc = cw.tc;
     tc.ntaps = cw.ntaps;
     tc.nchunks = (Ci + KCHUNK - 1) / KCHUNK;
-    tc.kch = tc.nchunks <= 3 ? tc.nchunks : 3;
-    SE_REQUIRE(tc.nchunks % tc.kch == 0, "chunk grouping");
     tc.NT = (Cout + 15) / 16 * 16;
+    tc.kch = tc_choose_kch(tc.ntaps * tc.nchunks, tc.NT);
     tc.n_tiles = 1;
     tc.img_rows = 0;
     tc.total_rows = (long long)tc.ntaps * tc.nchunks * tc.NT;
@@ -223,6 +229,7 @@ static int pack_layer(se_model* m, Layer& L) {
   const Spec& s = L.spec;
   L.Ci = stored_ci(s);
   L.is_head = (s.cin == 12);
+  L.is_stem = (s.k == 5);
   int rc = upload(m, L.b_host.data(), L.b_host.size() * 4, (void**)&L.bias);
   if (rc) return rc;
   if (L.is_head) {
@@ -233,11 +240,28 @@ static int pack_layer(se_model* m, Layer& L) {
     rc = upload(m, wh.data(), wh.size() * 4, (void**)&L.w_head);
     if (rc) return rc;
   }
+  if (L.is_stem) {
+    // 5x5 / pad 2 over <= 5 real channels: K per tap would be 3-5. Instead one GEMM-K chunk of 32 covers a
+    // window of 4 horizontally adjacent pixels x 8 packed channels; a kernel row needs two windows
+    // (kx 0..3 and kx 4 + three zero columns): 10 K-units instead of 25.
+    std::vector<EffTap> taps;
+    for (int ky = 0; ky < 5; ++ky)
+      for (int win = 0; win < 2; ++win) {
+        EffTap e;
+        e.dy = ky - 2;
+        e.dx = win * 4;           // window start in packed-buffer pixels: (x + PADL) + (win*4 - 2) = x + win*4
+        for (int pxl = 0; pxl < 4; ++pxl)
+          if (win * 4 + pxl < 5) e.src.push_back(SrcTap{ky, win * 4 + pxl, pxl * 8});
+        taps.push_back(e);
+      }
+    L.cls.resize(1);
+    return pack_class(m, L, taps, L.cls[0]);
+  }
   if (!s.deconv) {
     std::vector<EffTap> taps;
     const int p = s.rate * (s.k - 1) / 2;   // reference utils.py:21
     for (int ky = 0; ky < s.k; ++ky)
-      for (int kx = 0; kx < s.k; ++kx) taps.push_back(EffTap{ky * s.rate - p, kx * s.rate - p, {{ky, kx}}});
+      for (int kx = 0; kx < s.k; ++kx) taps.push_back(EffTap{ky * s.rate - p, kx * s.rate - p, {SrcTap{ky, kx, 0}}});
     L.cls.resize(1);
     return pack_class(m, L, taps, L.cls[0]);
   }
@@ -257,7 +281,7 @@ static int pack_layer(se_model* m, Layer& L) {
         std::vector<int> cols = (px == 0) ? (b == 0 ? std::vector<int>{0} : std::vector<int>{1, 2})
                                           : (b == 0 ? std::vector<int>{0, 1} : std::vector<int>{2});
         for (int r : rows)
-          for (int c : cols) e.src.push_back({r, c});
+          for (int c : cols) e.src.push_back(SrcTap{r, c, 0});
         taps.push_back(e);
       }
     ClassW& cw = L.cls[pc];
@@ -397,6 +421,12 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     memset(&cp, 0, sizeof(cp));
     cp.x = in.p; cp.in_dt = c.act_dt();
     cp.N = c.B; cp.Hi = in.H; cp.Wi = in.W; cp.Ci = L.Ci; cp.ldx = in.ld;
+    if (L.is_stem) {   // `in` is the packed 8-channel buffer with zero-padded rows of stem_wp(W) pixels
+      cp.ldx = 8;
+      cp.Wi = stem_wp(in.W) - 3;
+      cp.x_row_pitch = (long long)stem_wp(in.W) * 8;
+      cp.x_img_pitch = (long long)in.H * cp.x_row_pitch;
+    }
     cp.Ho = Ho; cp.Wo = Wo; cp.stride = s.deconv ? 1 : s.stride;
     cp.ntaps = cw.ntaps;
     memcpy(cp.dy, cw.dy, sizeof(cp.dy));
@@ -466,7 +496,7 @@ static int run_head(Ctx& c, char net, const std::string& name, const View& in, i
   Layer* L = find_ready(c.m, net, name);
   SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name + ": " + last_error());
   CK(head(in.p, c.act_dt(), L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
-          out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], c.stream));
+          out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, c.stream));
   return 0;
 }
 
@@ -510,8 +540,8 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cw.CoutP = Lpad;
     cw.w_direct = (float*)kbuf.p;
     cw.has_tc = tc;
-    cw.tc.data = kbuf.p; cw.tc.ntaps = 16; cw.tc.nchunks = C / 32; cw.tc.kch = (C / 32) <= 3 ? C / 32 : 1;
-    cw.tc.NT = 256; cw.tc.n_tiles = Lpad / 256; cw.tc.img_rows = 16 * (C / 32) * Lpad;
+    cw.tc.data = kbuf.p; cw.tc.ntaps = 16; cw.tc.nchunks = C / 32;
+    cw.tc.NT = 256; cw.tc.kch = tc_choose_kch(16 * (C / 32), 256); cw.tc.n_tiles = Lpad / 256; cw.tc.img_rows = 16 * (C / 32) * Lpad;
     cw.tc.total_rows = (long long)B * cw.tc.img_rows;
     cp.w_img_stride = (long long)16 * C * Lpad;
     CK(launch_conv(c, cp, cw, 2.0 * B * L * (double)L * C * 16));
@@ -552,7 +582,8 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cw.w_direct = (float*)vbuf.p + (tc ? 0 : pc * per_pc);
     cw.has_tc = tc && (C % 16 == 0);
     cw.tc.data = (const uint16_t*)vbuf.p + (tc ? pc * per_pc : 0);
-    cw.tc.ntaps = 4; cw.tc.nchunks = Lpad / 32; cw.tc.kch = 2; cw.tc.NT = C; cw.tc.n_tiles = 1;
+    cw.tc.ntaps = 4; cw.tc.nchunks = Lpad / 32; cw.tc.NT = C; cw.tc.n_tiles = 1;
+    cw.tc.kch = tc_choose_kch(4 * (Lpad / 32), C);
     cw.tc.img_rows = 4 * (Lpad / 32) * C;
     cw.tc.total_rows = (long long)B * cw.tc.img_rows;
     cp.w_img_stride = (long long)4 * Lpad * C;
@@ -571,8 +602,8 @@ static const std::initializer_list<const char*> kTrunk9 = {"conv1", "conv2_downs
 // binarised mask plane (mask1 > 0.5) when mask_bin != nullptr.
 static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, float* mask1, float* x_stage1, float* mask_bin) {
   const int dt = c.act_dt();
-  Buf in8 = c.get((size_t)c.B * H * W * 8 * c.esz());
-  CK(pack8(x, guide, nullptr, in8.p, dt, c.B, H, W, PACK_IMG_ONE, 1.0f, 0, c.stream));
+  Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * c.esz());
+  CK(pack8(x, guide, nullptr, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE, 1.0f, 0, c.stream));
   View x9;
   Buf b9;
   int rc = run_chain(c, 'M', with_prefix("", kTrunk9), View{in8.p, H, W, 8, 8}, true, in8, &x9, &b9);
@@ -616,16 +647,16 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   // ---- stage 1: coarse encoder + style ("warp-in") encoder -> 192-channel concat -> coarse decoder
   Buf cat1 = c.get((size_t)c.B * h * w * 192 * e);
   {
-    Buf in8 = c.get((size_t)c.B * H * W * 8 * e);
-    CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
+    Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
+    CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
     std::vector<std::string> names = with_prefix("", kTrunk9);
     names.push_back("conv10_atrous");
     int rc = run_chain(c, 'G', names, View{in8.p, H, W, 8, 8}, true, in8, nullptr, nullptr, cat1.p, 192, 0);
     if (rc) return rc;
   }
   {
-    Buf in8 = c.get((size_t)c.B * H * W * 8 * e);
-    CK(pack8(x2, guide, mask2, in8.p, dt, c.B, H, W, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M,
+    Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
+    CK(pack8(x2, guide, mask2, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M,
              opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f, 1, c.stream));
     std::vector<std::string> names = with_prefix("w", kTrunk9);
     names.push_back("wconv10_atrous");
@@ -639,13 +670,14 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     c.put(pooled);
     c.put(b);
   }
-  Buf xnow = c.get((size_t)c.B * H * W * 8 * e);
+  Buf xnow = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
   {
     View v16;
     Buf b16;
     int rc = run_chain(c, 'G', with_prefix("conv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}),
                        View{cat1.p, h, w, 192, 192}, true, cat1, &v16, &b16);
     if (rc) return rc;
+    CK(fill_zero(xnow.p, xnow.bytes, c.stream));   // zero pad pixels of the packed stage-2 input
     rc = run_head(c, 'G', "conv17", v16, HEAD_COARSE, x, mask, nullptr, x_stage1, nullptr, xnow.p);
     if (rc) return rc;
     c.put(b16);
@@ -857,9 +889,13 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
     const Spec& s = L->spec;
     const int dt = c.act_dt();
     const int Ci = L->is_head ? 12 : L->Ci;
-    Buf in = c.get((size_t)B * H * W * Ci * c.esz());
-    if (!c.dry && Ci != s.cin) SE_CUDA_OK(cudaMemsetAsync(in.p, 0, in.bytes, st));
-    CK(nchw_to_nhwc(x, in.p, dt, B, s.cin, H * W, Ci, 0, st));
+    Buf in = c.get(L->is_stem ? (size_t)B * H * stem_wp(W) * 8 * c.esz() : (size_t)B * H * W * Ci * c.esz());
+    if (L->is_stem) {
+      CK(fill_zero(in.p, in.bytes, st));
+      CK(nchw_to_stem8(x, in.p, dt, B, s.cin, H, W, stem_wp(W), STEM_PADL, st));
+    } else {
+      CK(nchw_to_nhwc(x, in.p, dt, B, s.cin, H * W, Ci, 0, st));
+    }
     int Ho, Wo;
     out_dims(s, H, W, &Ho, &Wo);
     if (L->is_head) {
@@ -881,7 +917,7 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
     } else {
       const int cg = s.cout / 2;
       Buf o = c.get((size_t)B * Ho * Wo * cg * c.esz());
-      int r = run_layer(c, *L, View{in.p, H, W, Ci, Ci}, o.p, cg, 0);
+      int r = run_layer(c, *L, View{in.p, H, W, L->is_stem ? 8 : Ci, L->is_stem ? 8 : Ci}, o.p, cg, 0);
       if (r) return r;
       CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, st));
       c.put(o);

@@ -23,11 +23,22 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // reference editline2_g.py:62 (cat[image, sketch]) and editline_g.py:120-135 (mask-mul + cat).
 template <typename T>
 __global__ void pack8_kernel(const float* __restrict__ img, const float* __restrict__ sketch, const float* __restrict__ mask,
-                             T* __restrict__ out, int B, int H, int W, int img_mode, float sketch_scale, int write_mask) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+                             T* __restrict__ out, int B, int H, int W, int Wp, int padl, int img_mode, float sketch_scale,
+                             int write_mask) {
+  // one thread per pixel of the PADDED row (Wp pixels, image at [padl, padl+W)); pads are written as zeros
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long HW = (long long)H * W;
-  if (i >= B * HW) return;
-  const long long b = i / HW, pix = i % HW;
+  if (j >= (long long)B * H * Wp) return;
+  const int xp = (int)(j % Wp);
+  const long long by = j / Wp;
+  const int x = xp - padl;
+  if (x < 0 || x >= W) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[j * 8 + c] = from_f<T>(0.0f);
+    return;
+  }
+  const long long b = by / H, pix = (by % H) * W + x;
+  const long long i = b * HW + pix;
   const float m = mask ? mask[i] : 0.0f;
   const float a = img_mode == PACK_IMG_ONE ? 1.0f : (img_mode == PACK_IMG_ONE_MINUS_M ? 1.0f - m : m);
   T v[8];
@@ -37,13 +48,13 @@ __global__ void pack8_kernel(const float* __restrict__ img, const float* __restr
   v[4] = from_f<T>(write_mask ? m : 0.0f);
   v[5] = v[6] = v[7] = from_f<T>(0.0f);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) out[i * 8 + c] = v[c];
+  for (int c = 0; c < 8; ++c) out[j * 8 + c] = v[c];
 }
 
-int pack8(const float* img, const float* sketch, const float* mask, void* out, int dt, int B, int H, int W, int img_mode,
-          float sketch_scale, int write_mask, cudaStream_t s) {
-  const long long n = (long long)B * H * W;
-  SE_DISPATCH_T(dt, (pack8_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(img, sketch, mask, (T*)out, B, H, W, img_mode, sketch_scale, write_mask)));
+int pack8(const float* img, const float* sketch, const float* mask, void* out, int dt, int B, int H, int W, int Wp, int padl,
+          int img_mode, float sketch_scale, int write_mask, cudaStream_t s) {
+  const long long n = (long long)B * H * Wp;
+  SE_DISPATCH_T(dt, (pack8_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(img, sketch, mask, (T*)out, B, H, W, Wp, padl, img_mode, sketch_scale, write_mask)));
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -59,7 +70,7 @@ template <typename T, int COUT>
 __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w /*[9][12][COUT]*/, const float* __restrict__ bias,
                             int B, int H, int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
                             const float* __restrict__ mask_soft, float* __restrict__ out_nchw, float* __restrict__ out2,
-                            T* __restrict__ out_pack8, int no_mask_coarse) {
+                            T* __restrict__ out_pack8, int no_mask_coarse, int Wp, int padl) {
   __shared__ float ws[9 * 12 * COUT + COUT];
   for (int i = threadIdx.x; i < 9 * 12 * COUT; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < COUT) ws[9 * 12 * COUT + threadIdx.x] = bias[threadIdx.x];
@@ -103,10 +114,10 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
       if (out_nchw) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
       const float xin = img[(b * 3 + o) * HW + pix] * (1.0f - m);
       const float v = no_mask_coarse ? t3[o] : (t3[o] * m + xin * (1.0f - m));
-      out_pack8[i * 8 + o] = from_f<T>(v);
+      out_pack8[((b * H + yy) * Wp + xx + padl) * 8 + o] = from_f<T>(v);
     }
 #pragma unroll
-    for (int o = COUT; o < 8; ++o) out_pack8[i * 8 + o] = from_f<T>(0.0f);
+    for (int o = COUT; o < 8; ++o) out_pack8[((b * H + yy) * Wp + xx + padl) * 8 + o] = from_f<T>(0.0f);
   } else {  // HEAD_FINE
     const float m = mask_soft[i];
 #pragma unroll
@@ -119,14 +130,14 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
 
 int head(const void* x, int dt, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
-         cudaStream_t s) {
+         int Wp, int padl, cudaStream_t s) {
   const long long n = (long long)B * H * W;
   SE_REQUIRE(cout == 1 || cout == 3, "head cout");
   SE_DISPATCH_T(dt, {
     if (cout == 1)
-      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse);
+      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl);
     else
-      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse);
+      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl);
   });
   SE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -395,6 +406,26 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
   const int c = (int)(r % C);
   const long long b = r / C;
   y[i] = to_f<T>(x[(b * HW + p) * ldx + choff + c]);
+}
+
+// NCHW fp32 [B,cin<=8,H,W] -> packed 8-channel rows of Wp pixels (image at [padl, padl+W)); pads/extra channels untouched
+template <typename T>
+__global__ void nchw_to_stem8_kernel(const float* __restrict__ x, T* __restrict__ y, int cin, int H, int W, int Wp, int padl, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % cin);
+  long long r = i / cin;
+  const int xx = (int)(r % W); r /= W;
+  const int yy = (int)(r % H);
+  const long long b = r / H;
+  y[((b * H + yy) * Wp + xx + padl) * 8 + c] = from_f<T>(x[((b * cin + c) * H + yy) * W + xx]);
+}
+int nchw_to_stem8(const float* x, void* y, int dt, int B, int cin, int H, int W, int Wp, int padl, cudaStream_t s) {
+  const long long total = (long long)B * cin * H * W;
+  SE_REQUIRE(cin <= 8, "stem input channels");
+  SE_DISPATCH_T(dt, (nchw_to_stem8_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, (T*)y, cin, H, W, Wp, padl, total)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s) {
