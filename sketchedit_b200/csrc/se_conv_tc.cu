@@ -63,6 +63,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// one lane of a fully converged warp (the warp stays converged: the compiler keeps addresses / descriptors
+// in uniform registers instead of broadcasting them lane by lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -201,8 +209,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int ksteps = total_q / p.kch;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================================================================== TMA producer
+    {
+      // ================================================================== TMA producer (warp converged, one lane issues)
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0, t_begin = clock64();
@@ -221,21 +229,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           t_wait += clock64() - tw;
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
           uint8_t* sB = sA + p.kch * A_CHUNK_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          for (int j = 0; j < p.kch; ++j) {
-            const int q = q0 + j;
-            const int t = q / p.nchunks, chunk = q - t * p.nchunks;
-            tma_load_4d(sA + j * A_CHUNK_BYTES, &tmA, &full_bar[stage], chunk * KCHUNK, x0 + p.dx[t], y0 + p.dy[t], img);
-            tma_load_2d(sB + j * b_chunk_bytes, &tmB, &full_bar[stage], 0, wrow0 + q * p.w_rows_tc);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            for (int j = 0; j < p.kch; ++j) {
+              const int q = q0 + j;
+              const int t = q / p.nchunks, chunk = q - t * p.nchunks;
+              tma_load_4d(sA + j * A_CHUNK_BYTES, &tmA, &full_bar[stage], chunk * KCHUNK, x0 + p.dx[t], y0 + p.dy[t], img);
+              tma_load_2d(sB + j * b_chunk_bytes, &tmB, &full_bar[stage], 0, wrow0 + q * p.w_rows_tc);
+            }
           }
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================================================================== MMA issuer
+    {
+      // ================================================================== MMA issuer (warp converged, one lane issues)
       // instruction descriptor: D=f32, A=B=bf16, K-major both, N = NT, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       int stage = 0;
@@ -257,20 +268,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sB = sA + p.kch * A_CHUNK_BYTES;
-          for (int j = 0; j < p.kch; ++j) {
-#pragma unroll
-            for (int k = 0; k < KCHUNK / 16; ++k) {
-              const uint64_t adesc = make_kmajor_sw64_desc(sA + j * A_CHUNK_BYTES + k * 32);
-              const uint64_t bdesc = make_kmajor_sw64_desc(sB + j * b_chunk_bytes + k * 32);
-              umma_bf16(tmem_d, adesc, bdesc, idesc, (ks | j | k) ? 1u : 0u);
+          if (elect_one()) {
+            // descriptors differ only in the 14-bit start-address field: advance by (bytes >> 4)
+            uint64_t adesc = make_kmajor_sw64_desc(sA);
+            uint64_t bdesc = make_kmajor_sw64_desc(sB);
+            const uint32_t a_step = A_CHUNK_BYTES >> 4, b_step = (uint32_t)b_chunk_bytes >> 4;
+            for (int j = 0; j < p.kch; ++j) {
+              umma_bf16(tmem_d, adesc, bdesc, idesc, (ks | j) ? 1u : 0u);
+              umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);       // second K=16 half: +32 B
+              adesc += a_step;
+              bdesc += b_step;
             }
+            umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+            if (ks == ksteps - 1) umma_commit(&tmem_full[as]);    // accumulator complete
           }
-          umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-          if (ks == ksteps - 1) umma_commit(&tmem_full[as]);    // accumulator complete
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
     }
   } else if (warp >= 4) {
     // ==================================================================== epilogue
