@@ -1,10 +1,11 @@
 // tcgen05 implicit-GEMM convolution for sm_100a.
 //
 // One persistent CTA per SM. Per output tile (8 x 16 positions of one image = UMMA M = 128) the
-// K loop walks (tap, 32-channel chunk): the A operand is a TMA *tiled* box of the NHWC input shifted
-// by the tap offset (zero padding = TMA out-of-bounds fill; stride-2 = TMA element strides), the
-// B operand is a [NT x 32] K-major slab of the packed weights. Both land in SWIZZLE_64B shared
-// memory and feed tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulating into one of two TMEM
+// K loop walks (tap, channel chunk): the A operand is a TMA *tiled* box of the NHWC input shifted by the
+// tap offset (zero padding = TMA out-of-bounds fill; stride-2 = TMA element strides) -- 64-channel chunks
+// land as 128 B rows (SWIZZLE_128B), a trailing 32-channel chunk as 64 B rows (SWIZZLE_64B); the B operand
+// of a whole pipeline stage is ONE linear cp.async.bulk of the pre-swizzled weight image. Both feed
+// tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulating into one of two TMEM
 // accumulator stages; four epilogue warps drain the other stage (tcgen05.ld), apply
 // bias + ELU/ReLU x sigmoid gating (reference models/networks/utils.py:25-33) or the linear
 // epilogue of the attention GEMMs, and store NHWC.
@@ -56,11 +57,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
+// linear global -> shared bulk copy (bytes % 16 == 0), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // one lane of a fully converged warp (the warp stays converged: the compiler keeps addresses / descriptors
@@ -141,31 +142,34 @@ __device__ __forceinline__ void store_row_f32(float* o, const float (&r)[16], in
   }
 }
 
-// K-major, SWIZZLE_64B operand tile: rows of 64 B, 8-row atoms 512 B apart (cute::UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+// K-major operand tiles (cute::UMMA::SmemDescriptor): rows of 128 B (SWIZZLE_128B, 8-row atoms 1024 B apart)
+// or rows of 64 B (SWIZZLE_64B, atoms 512 B apart). Only the 14-bit start-address field changes per MMA.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, bool sw128) {
   uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address        bits [0,14)
-  d |= (uint64_t)0 << 16;                         // leading byte offset  bits [16,30)  (unused: one atom along K)
-  d |= (uint64_t)(512 >> 4) << 32;                // stride byte offset   bits [32,46)
-  d |= (uint64_t)1 << 46;                         // descriptor version 1 (sm_100)
-  d |= (uint64_t)4 << 61;                         // layout type: SWIZZLE_64B
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);               // start address        bits [0,14)
+  d |= (uint64_t)((sw128 ? 1024 : 512) >> 4) << 32;           // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                                     // descriptor version 1 (sm_100)
+  d |= (uint64_t)(sw128 ? 2 : 4) << 61;                       // layout type: SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-constexpr int A_CHUNK_BYTES = TILE_M * KCHUNK * 2;   // 8192
+constexpr int A64_BYTES = TILE_M * 128;              // 64-channel A unit
+constexpr int A32_BYTES = TILE_M * 64;               // 32-channel A unit
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;                      // TMEM columns between the two accumulator stages
 constexpr int MAX_STAGES = 8;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmA32, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A kch chunks | B kch chunks] then barriers, tmem ptr, bias
+  // carve: [stages][A64 x r64 | A32 x r32 | B image] then barriers, tmem ptr, bias
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_chunk_bytes = p.NT * KCHUNK * 2;
-  const int stage_bytes = p.kch * (A_CHUNK_BYTES + b_chunk_bytes);
+  const int a_bytes = p.r64 * A64_BYTES + p.r32 * A32_BYTES;
+  const int b64_bytes = p.NT * 128, b32_bytes = p.NT * 64;
+  const int b_bytes = p.r64 * b64_bytes + p.r32 * b32_bytes;
+  const int stage_bytes = a_bytes + b_bytes;
   uint8_t* tail = smem + (size_t)p.num_stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -178,8 +182,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA64)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA32)) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
@@ -205,89 +209,99 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.N * tiles_per_img * p.n_tiles;
-  const int total_q = p.ntaps * p.nchunks;   // flattened (tap, chunk) units; kch consecutive units per stage
-  const int ksteps = total_q / p.kch;
+  const int ksteps = p.ksteps;
 
   if (warp == 0) {
-    {
-      // ================================================================== TMA producer (warp converged, one lane issues)
-      int stage = 0;
-      uint32_t phase = 0;
-      long long t_wait = 0, t_begin = clock64();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int rest = tile / p.n_tiles;
-        const int tx = rest % p.tiles_x;
-        rest /= p.tiles_x;
-        const int ty = rest % p.tiles_y;
-        const int img = rest / p.tiles_y;
-        const int x0 = tx * TILE_W * p.stride, y0 = ty * TILE_H * p.stride;
-        const int wrow0 = img * p.w_img_rows + nt * p.NT;
-        for (int q0 = 0; q0 < total_q; q0 += p.kch) {
-          const long long tw = clock64();
-          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          t_wait += clock64() - tw;
-          uint8_t* sA = smem + (size_t)stage * stage_bytes;
-          uint8_t* sB = sA + p.kch * A_CHUNK_BYTES;
-          if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-            for (int j = 0; j < p.kch; ++j) {
-              const int q = q0 + j;
-              const int t = q / p.nchunks, chunk = q - t * p.nchunks;
-              tma_load_4d(sA + j * A_CHUNK_BYTES, &tmA, &full_bar[stage], chunk * KCHUNK, x0 + p.dx[t], y0 + p.dy[t], img);
-              tma_load_2d(sB + j * b_chunk_bytes, &tmB, &full_bar[stage], 0, wrow0 + q * p.w_rows_tc);
-            }
+    // ==================================================================== TMA producer (warp converged, one lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    long long t_wait = 0, t_begin = clock64();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int rest = tile / p.n_tiles;
+      const int tx = rest % p.tiles_x;
+      rest /= p.tiles_x;
+      const int ty = rest % p.tiles_y;
+      const int img = rest / p.tiles_y;
+      const int x0 = tx * TILE_W * p.stride, y0 = ty * TILE_H * p.stride;
+      const uint8_t* wsrc = p.w + (size_t)img * p.w_img_bytes + (size_t)nt * ksteps * b_bytes;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const long long tw = clock64();
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        t_wait += clock64() - tw;
+        uint8_t* sA = smem + (size_t)stage * stage_bytes;
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          bulk_load_1d(sA + a_bytes, wsrc + (size_t)ks * b_bytes, (uint32_t)b_bytes, &full_bar[stage]);
+          for (int j = 0; j < p.r64; ++j) {
+            const int u = ks * p.r64 + j;
+            const int t = u / p.n64, chunk = u - t * p.n64;
+            tma_load_4d(sA + j * A64_BYTES, &tmA64, &full_bar[stage], chunk * 64, x0 + p.dx[t], y0 + p.dy[t], img);
           }
-          __syncwarp();
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          for (int j = 0; j < p.r32; ++j) {
+            const int t = ks * p.r32 + j;     // n32 == 1: one 32-wide unit per tap
+            tma_load_4d(sA + p.r64 * A64_BYTES + j * A32_BYTES, &tmA32, &full_bar[stage], p.n64 * 64, x0 + p.dx[t], y0 + p.dy[t], img);
+          }
         }
+        __syncwarp();
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
     }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
   } else if (warp == 1) {
-    {
-      // ================================================================== MMA issuer (warp converged, one lane issues)
-      // instruction descriptor: D=f32, A=B=bf16, K-major both, N = NT, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int iter = 0;
-      long long t_wfull = 0, t_wtmem = 0, t_begin = clock64();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-        const int as = iter & 1;
-        const uint32_t aphase = (iter >> 1) & 1;
-        long long tw = clock64();
-        mbar_wait(&tmem_empty[as], aphase ^ 1, 2);
-        t_wtmem += clock64() - tw;
+    // ==================================================================== MMA issuer (warp converged, one lane issues)
+    // instruction descriptor: D=f32, A=B=bf16, K-major both, N = NT, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    long long t_wfull = 0, t_wtmem = 0, t_begin = clock64();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      long long tw = clock64();
+      mbar_wait(&tmem_empty[as], aphase ^ 1, 2);
+      t_wtmem += clock64() - tw;
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        tw = clock64();
+        mbar_wait(&full_bar[stage], phase, 3);
+        t_wfull += clock64() - tw;
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          tw = clock64();
-          mbar_wait(&full_bar[stage], phase, 3);
-          t_wfull += clock64() - tw;
-          tc_fence_after();
-          const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sB = sA + p.kch * A_CHUNK_BYTES;
-          if (elect_one()) {
-            // descriptors differ only in the 14-bit start-address field: advance by (bytes >> 4)
-            uint64_t adesc = make_kmajor_sw64_desc(sA);
-            uint64_t bdesc = make_kmajor_sw64_desc(sB);
-            const uint32_t a_step = A_CHUNK_BYTES >> 4, b_step = (uint32_t)b_chunk_bytes >> 4;
-            for (int j = 0; j < p.kch; ++j) {
-              umma_bf16(tmem_d, adesc, bdesc, idesc, (ks | j) ? 1u : 0u);
-              umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);       // second K=16 half: +32 B
-              adesc += a_step;
-              bdesc += b_step;
+        const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sB = sA + a_bytes;
+        if (elect_one()) {
+          uint32_t acc = ks ? 1u : 0u;
+          // 64-channel units: four K=16 MMAs each, +32 B (= +2 in the descriptor) per step
+          uint64_t ad = make_kmajor_desc(sA, true), bd = make_kmajor_desc(sB, true);
+          for (int j = 0; j < p.r64; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, acc);
+              acc = 1u;
             }
-            umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-            if (ks == ksteps - 1) umma_commit(&tmem_full[as]);    // accumulator complete
+            ad += A64_BYTES >> 4;
+            bd += (uint32_t)b64_bytes >> 4;
           }
-          __syncwarp();
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          // trailing 32-channel units: two K=16 MMAs each
+          ad = make_kmajor_desc(sA + p.r64 * A64_BYTES, false);
+          bd = make_kmajor_desc(sB + p.r64 * b64_bytes, false);
+          for (int j = 0; j < p.r32; ++j) {
+            umma_bf16(tmem_d, ad, bd, idesc, acc);
+            umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+            acc = 1u;
+            ad += A32_BYTES >> 4;
+            bd += (uint32_t)b32_bytes >> 4;
+          }
+          umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+          if (ks == ksteps - 1) umma_commit(&tmem_full[as]);    // accumulator complete
         }
+        __syncwarp();
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
     }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
   } else if (warp >= 4) {
     // ==================================================================== epilogue
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
@@ -392,16 +406,33 @@ static EncodeTiledFn get_encode_fn() {
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
 
-int tc_smem_budget() { return 200 * 1024; }
+static int tc_smem_budget() { return 200 * 1024; }
 
-// chunks per pipeline stage: the largest divisor of total_q whose stage stays under ~48 KB (SE_TC_STAGE_KB)
-int tc_choose_kch(int total_q, int NT) {
+void tc_choose_stage(TcWeights* w) {
   static int cap_kb = getenv("SE_TC_STAGE_KB") ? atoi(getenv("SE_TC_STAGE_KB")) : 48;
-  const int unit = A_CHUNK_BYTES + NT * KCHUNK * 2;
-  int best = 1;
-  for (int k = 1; k <= 8 && k <= total_q; ++k)
-    if (total_q % k == 0 && k * unit <= cap_kb * 1024) best = k;
-  return best;
+  const int u64 = A64_BYTES + w->NT * 128, u32 = A32_BYTES + w->NT * 64;
+  if (w->n64 > 0 && w->n32 > 0) {
+    // mixed taps (e.g. 96 channels = 64 + 32): a stage holds whole taps
+    int best = 1;
+    for (int t = 1; t <= 4 && t <= w->ntaps; ++t)
+      if (w->ntaps % t == 0 && t * (w->n64 * u64 + u32) <= cap_kb * 1024) best = t;
+    w->r64 = best * w->n64;
+    w->r32 = best;
+  } else if (w->n64 > 0) {
+    const int total = w->ntaps * w->n64;
+    int best = 1;
+    for (int k = 1; k <= 8 && k <= total; ++k)
+      if (total % k == 0 && k * u64 <= cap_kb * 1024) best = k;
+    w->r64 = best;
+    w->r32 = 0;
+  } else {
+    const int total = w->ntaps * w->n32;
+    int best = 1;
+    for (int k = 1; k <= 8 && k <= total; ++k)
+      if (total % k == 0 && k * u32 <= cap_kb * 1024) best = k;
+    w->r64 = 0;
+    w->r32 = best;
+  }
 }
 
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes) {
@@ -410,10 +441,13 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   SE_REQUIRE(c.in_dt == DT_BF16, "tcgen05 path reads bf16 activations");
   SE_REQUIRE(c.ldx % 8 == 0, "input pixel pitch must be a multiple of 8 elements (16 B TMA stride)");
   SE_REQUIRE((reinterpret_cast<uintptr_t>(c.x) & 15) == 0, "input base must be 16 B aligned");
+  SE_REQUIRE((reinterpret_cast<uintptr_t>(w.data) & 15) == 0 && w.img_bytes % 16 == 0, "weight image must be 16 B aligned");
   SE_REQUIRE(c.ntaps <= MAX_TAPS && c.ntaps == w.ntaps, "tap count mismatch");
   SE_REQUIRE(w.NT % 16 == 0 && w.NT >= 16 && w.NT <= 256, "NT");
-  SE_REQUIRE((w.ntaps * w.nchunks) % w.kch == 0, "kch must divide ntaps*nchunks");
-  SE_REQUIRE(w.nchunks * KCHUNK >= c.Ci, "weights do not cover Ci");
+  SE_REQUIRE(w.n32 <= 1 && (w.n64 > 0 || w.n32 > 0), "chunking");
+  SE_REQUIRE(w.n64 * 64 + w.n32 * 32 >= c.Ci, "weights do not cover Ci");
+  SE_REQUIRE((w.n64 == 0 || (w.r64 > 0 && (w.ntaps * w.n64) % w.r64 == 0)) && (w.n32 == 0 || (w.r32 > 0 && w.ntaps % w.r32 == 0)), "stage grouping");
+  SE_REQUIRE(w.n64 == 0 || w.n32 == 0 || w.ntaps * w.n64 / w.r64 == w.ntaps / w.r32, "mixed stages must hold whole taps");
   SE_REQUIRE(c.stride >= 1 && c.stride <= 2, "stride");
   p.N = c.N; p.Ho = c.Ho; p.Wo = c.Wo;
   p.tiles_x = (c.Wo + TILE_W - 1) / TILE_W;
@@ -423,9 +457,10 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   p.ntaps = c.ntaps;
   memcpy(p.dy, c.dy, sizeof(p.dy));
   memcpy(p.dx, c.dx, sizeof(p.dx));
-  p.nchunks = w.nchunks; p.kch = w.kch; p.NT = w.NT;
-  p.w_rows_tc = w.n_tiles * w.NT;
-  p.w_img_rows = w.img_rows;
+  p.n64 = w.n64; p.n32 = w.n32; p.r64 = w.n64 ? w.r64 : 0; p.r32 = w.n32 ? w.r32 : 0; p.NT = w.NT;
+  p.ksteps = tc_ksteps(w);
+  p.w_img_bytes = w.img_bytes;
+  p.w = reinterpret_cast<const uint8_t*>(w.data);
   p.bias = c.bias; p.Cout = c.Cout;
   p.y = c.y; p.out_dt = c.out_dt; p.Hout = c.Hout; p.Wout = c.Wout; p.ldo = c.ldo; p.choff = c.choff;
   p.osy = c.osy; p.ooy = c.ooy; p.osx = c.osx; p.oox = c.oox;
@@ -433,13 +468,27 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   if (c.epi != EPI_LINEAR) {
     SE_REQUIRE(w.n_tiles == 1 && c.Cout % 2 == 0 && c.out_dt == DT_BF16, "gated epilogue needs one N tile, even Cout, bf16 out");
   }
-  const int stage_bytes = w.kch * (A_CHUNK_BYTES + w.NT * KCHUNK * 2);
+  const int stage_bytes = p.r64 * (A64_BYTES + w.NT * 128) + p.r32 * (A32_BYTES + w.NT * 64);
   int stages = tc_smem_budget() / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   SE_REQUIRE(stages >= 2, "pipeline needs >= 2 stages");
   p.num_stages = stages;
   *smem_bytes = 1024 + stages * stage_bytes + (2 * MAX_STAGES + 4) * 8 + 16 + (p.n_tiles * p.NT + 32) * 4 + 64;
   *out = p;
+  return 0;
+}
+
+static int encode_act_map(EncodeTiledFn enc, CUtensorMap* tm, const ConvParams& c, int inner, CUtensorMapSwizzle swz) {
+  // activations: (C, W, H, N), box (inner, 16*s, 8*s, 1) walked with element strides (1, s, s, 1)
+  const long long row_pitch = c.x_row_pitch ? c.x_row_pitch : (long long)c.Wi * c.ldx;
+  const long long img_pitch = c.x_img_pitch ? c.x_img_pitch : (long long)c.Hi * row_pitch;
+  cuuint64_t dims[4] = {(cuuint64_t)c.Ci, (cuuint64_t)c.Wi, (cuuint64_t)c.Hi, (cuuint64_t)c.N};
+  cuuint64_t strides[3] = {(cuuint64_t)c.ldx * 2, (cuuint64_t)row_pitch * 2, (cuuint64_t)img_pitch * 2};
+  cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)(TILE_W * c.stride), (cuuint32_t)(TILE_H * c.stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed, CUresult=" + std::to_string((int)r));
   return 0;
 }
 
@@ -459,30 +508,12 @@ int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
   }
   SE_REQUIRE(smem_bytes <= g_smem_optin, "shared memory plan exceeds the opt-in limit");
 
-  CUtensorMap tmA, tmB;
-  {
-    // activations: (C, W, H, N), box (32, 16*s, 8*s, 1) walked with element strides (1, s, s, 1)
-    cuuint64_t dims[4] = {(cuuint64_t)c.Ci, (cuuint64_t)c.Wi, (cuuint64_t)c.Hi, (cuuint64_t)c.N};
-    const long long row_pitch = c.x_row_pitch ? c.x_row_pitch : (long long)c.Wi * c.ldx;
-    const long long img_pitch = c.x_img_pitch ? c.x_img_pitch : (long long)c.Hi * row_pitch;
-    cuuint64_t strides[3] = {(cuuint64_t)c.ldx * 2, (cuuint64_t)row_pitch * 2, (cuuint64_t)img_pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)KCHUNK, (cuuint32_t)(TILE_W * c.stride), (cuuint32_t)(TILE_H * c.stride), 1};
-    cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
-    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.x), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed, CUresult=" + std::to_string((int)r));
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)KCHUNK, (cuuint64_t)w.total_rows};
-    cuuint64_t strides[1] = {(cuuint64_t)KCHUNK * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KCHUNK, (cuuint32_t)w.NT};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w.data), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed, CUresult=" + std::to_string((int)r));
-  }
+  CUtensorMap tmA64, tmA32;
+  rc = encode_act_map(enc, &tmA64, c, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = encode_act_map(enc, &tmA32, c, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+
   const int total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_tiles;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
   static const bool dbg_on = getenv("SE_TC_DEBUG") != nullptr;
@@ -492,7 +523,7 @@ int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
     SE_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 8 * 8 * 1024, stream));
     p.dbg = dbg_buf;
   }
-  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA64, tmA32, p);
   SE_CUDA_OK(cudaGetLastError());
   if (dbg_on) {
     SE_CUDA_OK(cudaStreamSynchronize(stream));
@@ -502,8 +533,8 @@ int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
     for (int b = 0; b < grid; ++b)
       for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 8 + k] / grid;
     fprintf(stderr,
-            "[tc] N=%d %dx%d Ci=%d s=%d taps=%d NT=%d kch=%d stages=%d tiles=%d grid=%d | prod wait_empty %.0f/%.0f | mma wait_full %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f (cycles, mean per CTA)\n",
-            c.N, c.Ho, c.Wo, c.Ci, c.stride, c.ntaps, p.NT, p.kch, p.num_stages, total_tiles, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+            "[tc] N=%d %dx%d Ci=%d s=%d taps=%d NT=%d n64=%d n32=%d r64=%d r32=%d stages=%d tiles=%d grid=%d | prod wait_empty %.0f/%.0f | mma wait_full %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f (cycles, mean per CTA)\n",
+            c.N, c.Ho, c.Wo, c.Ci, c.stride, c.ntaps, p.NT, p.n64, p.n32, p.r64, p.r32, p.num_stages, total_tiles, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
   }
   return 0;
 }

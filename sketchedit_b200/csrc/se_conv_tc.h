@@ -4,19 +4,40 @@
 
 namespace se {
 
-// Packed bf16 weights for the tcgen05 path:
-//   row(img, tap, chunk, n) = img*img_rows + (tap*nchunks + chunk) * (n_tiles*NT) + n ,  32 K-elements per row
-// i.e. a 2-D [total_rows x 32] K-major matrix that TMA slices into [NT x 32] SWIZZLE_64B slabs.
+// The GEMM K axis of one tap is cut into `n64` chunks of 64 channels (128 B rows, SWIZZLE_128B) followed by
+// `n32` (0 or 1) chunk of 32 channels (64 B rows, SWIZZLE_64B); channels beyond Ci are zero (TMA OOB fill).
+// One pipeline stage holds r64 consecutive 64-wide units and r32 consecutive 32-wide units.
+//
+// Weights are stored in global memory as the exact shared-memory image of each stage (already swizzled),
+// so a stage's B operand is ONE linear cp.async.bulk:
+//   image(img, n_tile, kstep) at  data + img*img_bytes + (n_tile*ksteps + kstep) * stage_b_bytes
+//   = r64 x [NT rows x 128 B] followed by r32 x [NT rows x 64 B]
 struct TcWeights {
-  const void* data = nullptr;   // device, bf16
+  const void* data = nullptr;   // device, bf16, pre-swizzled stage images
   int ntaps = 0;
-  int nchunks = 0;              // 32-channel chunks per tap (Cin padded with zeros)
-  int kch = 1;                  // (tap,chunk) units per pipeline stage; divides ntaps*nchunks
+  int n64 = 0, n32 = 0;         // chunks per tap
+  int r64 = 0, r32 = 0;         // units per pipeline stage
   int NT = 0;                   // GEMM N per tile (Cout padded to 16), <= 256
   int n_tiles = 1;
-  int img_rows = 0;             // rows per image for per-image weights (attention), 0 = shared
-  long long total_rows = 0;
+  long long img_bytes = 0;      // bytes between images for per-image weights (attention), 0 = shared
 };
+
+inline int tc_ksteps(const TcWeights& w) { return w.n64 ? w.ntaps * w.n64 / w.r64 : w.ntaps * w.n32 / w.r32; }
+inline int tc_stage_b_bytes(const TcWeights& w) { return w.NT * (w.r64 * 128 + w.r32 * 64); }
+inline long long tc_weight_bytes_per_image(const TcWeights& w) { return (long long)w.n_tiles * tc_ksteps(w) * tc_stage_b_bytes(w); }
+
+// byte offset of (row r, byte kb within the row) inside a K-major operand tile with RB-byte rows whose base is
+// 1024 B aligned: the 128B / 64B TMA+UMMA swizzle (cute Swizzle<3,4,3> / Swizzle<2,4,3>).
+__host__ __device__ inline uint32_t tc_swizzle_offset(int r, int kb, int RB) {
+  uint32_t off = (uint32_t)r * RB + kb;
+  return off ^ (((off >> 7) & (RB == 128 ? 7u : 3u)) << 4);
+}
+
+// where element (unit kind/index, n, k) of a stage lands inside the stage's B image
+__host__ __device__ inline uint32_t tc_b_image_offset(int NT, int r64, bool is64, int j, int n, int k) {
+  if (is64) return (uint32_t)j * NT * 128 + tc_swizzle_offset(n, k * 2, 128);
+  return (uint32_t)r64 * NT * 128 + (uint32_t)j * NT * 64 + tc_swizzle_offset(n, k * 2, 64);
+}
 
 struct TcParams {
   int N, Ho, Wo;
@@ -24,8 +45,10 @@ struct TcParams {
   int stride;
   int ntaps;
   int8_t dy[MAX_TAPS], dx[MAX_TAPS];
-  int nchunks, kch, NT;
-  int w_rows_tc, w_img_rows;
+  int n64, n32, r64, r32, NT;
+  int ksteps;
+  long long w_img_bytes;
+  const uint8_t* w;
   int num_stages;
   const float* bias;
   int Cout;
@@ -39,7 +62,8 @@ struct TcParams {
   unsigned long long* dbg;   // optional per-CTA role timers (SE_TC_DEBUG=1)
 };
 
-int tc_choose_kch(int total_q, int NT);
+// pick (r64, r32) for a layer: as many units per stage as fit ~48 KB (SE_TC_STAGE_KB)
+void tc_choose_stage(TcWeights* w);
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes);
 int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream);
 

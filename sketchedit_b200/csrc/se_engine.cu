@@ -150,11 +150,11 @@ struct se_model {
 
 namespace se {
 
-// 5x5 stems read an 8-channel packed input through overlapping 4-pixel windows: 32 virtual channels
+// 5x5 stems read an 8-channel packed input through overlapping 8-pixel windows: 64 virtual channels
 // (pixel pitch 8 elements), see pack_layer / run_layer.
 constexpr int STEM_PADL = 2;                       // zero pixels left of the image in the packed buffer
 static inline int stem_wp(int W) { return W + 8; } // packed row length (2 left + 6 right zero pixels)
-static int stored_ci(const Spec& s) { return s.k == 5 ? 32 : s.cin; }
+static int stored_ci(const Spec& s) { return s.k == 5 ? 64 : s.cin; }
 
 static int upload(se_model* m, const void* host, size_t bytes, void** dev) {
   SE_CUDA_OK(cudaMalloc(dev, bytes));
@@ -203,22 +203,33 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
   if (cw.has_tc) {
     TcWeights& tc = cw.tc;
     tc.ntaps = cw.ntaps;
-    tc.nchunks = (Ci + KCHUNK - 1) / KCHUNK;
+    tc.n64 = Ci / 64;
+    int rem = Ci - 64 * tc.n64;
+    if (rem > 32) { ++tc.n64; rem = 0; }
+    tc.n32 = rem > 0 ? 1 : 0;
     tc.NT = (Cout + 15) / 16 * 16;
-    tc.kch = tc_choose_kch(tc.ntaps * tc.nchunks, tc.NT);
     tc.n_tiles = 1;
-    tc.img_rows = 0;
-    tc.total_rows = (long long)tc.ntaps * tc.nchunks * tc.NT;
-    std::vector<uint16_t> wt((size_t)tc.total_rows * KCHUNK, 0);
-    for (int t = 0; t < tc.ntaps; ++t)
-      for (int ch = 0; ch < tc.nchunks; ++ch)
+    tc.img_bytes = 0;
+    tc_choose_stage(&tc);
+    // the exact (swizzled) shared-memory image of every pipeline stage, see se_conv_tc.h
+    const int ksteps = tc_ksteps(tc), sb = tc_stage_b_bytes(tc);
+    std::vector<uint16_t> img((size_t)ksteps * sb / 2, 0);
+    auto wv = [&](int t, int ci, int n) -> uint16_t { return ci < Ci ? f32_to_bf16_rn(weff[((size_t)t * Ci + ci) * Cout + n]) : (uint16_t)0; };
+    for (int ks = 0; ks < ksteps; ++ks) {
+      uint16_t* base = img.data() + (size_t)ks * sb / 2;
+      for (int j = 0; j < tc.r64 && tc.n64; ++j) {
+        const int u = ks * tc.r64 + j, t = u / tc.n64, chunk = u % tc.n64;
         for (int n = 0; n < Cout; ++n)
-          for (int kk = 0; kk < KCHUNK; ++kk) {
-            const int ci = ch * KCHUNK + kk;
-            if (ci < Ci) wt[(((size_t)t * tc.nchunks + ch) * tc.NT + n) * KCHUNK + kk] = f32_to_bf16_rn(weff[((size_t)t * Ci + ci) * Cout + n]);
-          }
+          for (int k = 0; k < 64; ++k) base[tc_b_image_offset(tc.NT, tc.r64, true, j, n, k) / 2] = wv(t, chunk * 64 + k, n);
+      }
+      for (int j = 0; j < tc.r32 && tc.n32; ++j) {
+        const int t = ks * tc.r32 + j;
+        for (int n = 0; n < Cout; ++n)
+          for (int k = 0; k < 32; ++k) base[tc_b_image_offset(tc.NT, tc.n64 ? tc.r64 : 0, false, j, n, k) / 2] = wv(t, tc.n64 * 64 + k, n);
+      }
+    }
     void* d = nullptr;
-    int rc = upload(m, wt.data(), wt.size() * 2, &d);
+    int rc = upload(m, img.data(), img.size() * 2, &d);
     if (rc) return rc;
     tc.data = d;
   }
@@ -241,19 +252,18 @@ static int pack_layer(se_model* m, Layer& L) {
     if (rc) return rc;
   }
   if (L.is_stem) {
-    // 5x5 / pad 2 over <= 5 real channels: K per tap would be 3-5. Instead one GEMM-K chunk of 32 covers a
-    // window of 4 horizontally adjacent pixels x 8 packed channels; a kernel row needs two windows
-    // (kx 0..3 and kx 4 + three zero columns): 10 K-units instead of 25.
+    // 5x5 / pad 2 over <= 5 real channels: K per tap would be 3-5. Instead one 64-wide GEMM-K chunk covers a
+    // window of 8 horizontally adjacent pixels x 8 packed channels (kernel columns 0..4 + three zero columns):
+    // 5 K-units (one per kernel row) instead of 25 taps. Window start in packed-buffer pixels:
+    // (x + STEM_PADL) - 2 = x, so dx = 0.
     std::vector<EffTap> taps;
-    for (int ky = 0; ky < 5; ++ky)
-      for (int win = 0; win < 2; ++win) {
-        EffTap e;
-        e.dy = ky - 2;
-        e.dx = win * 4;           // window start in packed-buffer pixels: (x + PADL) + (win*4 - 2) = x + win*4
-        for (int pxl = 0; pxl < 4; ++pxl)
-          if (win * 4 + pxl < 5) e.src.push_back(SrcTap{ky, win * 4 + pxl, pxl * 8});
-        taps.push_back(e);
-      }
+    for (int ky = 0; ky < 5; ++ky) {
+      EffTap e;
+      e.dy = ky - 2;
+      e.dx = 0;
+      for (int pxl = 0; pxl < 5; ++pxl) e.src.push_back(SrcTap{ky, pxl, pxl * 8});
+      taps.push_back(e);
+    }
     L.cls.resize(1);
     return pack_class(m, L, taps, L.cls[0]);
   }
@@ -423,7 +433,7 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     cp.N = c.B; cp.Hi = in.H; cp.Wi = in.W; cp.Ci = L.Ci; cp.ldx = in.ld;
     if (L.is_stem) {   // `in` is the packed 8-channel buffer with zero-padded rows of stem_wp(W) pixels
       cp.ldx = 8;
-      cp.Wi = stem_wp(in.W) - 3;
+      cp.Wi = stem_wp(in.W) - 7;
       cp.x_row_pitch = (long long)stem_wp(in.W) * 8;
       cp.x_img_pitch = (long long)in.H * cp.x_row_pitch;
     }
@@ -508,7 +518,7 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   const int B = c.B, h = f.H, w = f.W, C = f.C;
   SE_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "attention map must be even-sized and >= 4");
   const int hs = (h - 4) / 2 + 1, ws = (w - 4) / 2 + 1, L = hs * ws;
-  const int Lpad = (L + 255) / 256 * 256;
+  const int Lpad = (L + 127) / 128 * 128;
   const bool tc = (c.prec == SE_PREC_BF16_TC) && (C % 32 == 0) && (f.ld % 8 == 0);
   const int dt = c.act_dt();
 
@@ -518,10 +528,15 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   CK(cam_colmask(mask_s, (float*)colm.p, B, h, w, hs, ws, 0.1f, c.stream));
 
   // ---- keys
-  const size_t kelems = (size_t)B * 16 * C * Lpad;
-  Buf kbuf = c.get(kelems * (tc ? 2 : 4));
+  TcWeights ktc;   // S = Q K^T: 16 taps of C channels, N tiles of 128 keys
+  ktc.ntaps = 16; ktc.n64 = C / 64; ktc.n32 = (C % 64) ? 1 : 0; ktc.NT = 128; ktc.n_tiles = Lpad / 128;
+  tc_choose_stage(&ktc);
+  ktc.img_bytes = tc ? tc_weight_bytes_per_image(ktc) : 0;
+  const size_t kbytes = tc ? (size_t)B * ktc.img_bytes : (size_t)B * 16 * C * Lpad * 4;
+  Buf kbuf = c.get(kbytes);
   SE_REQUIRE(f.ld == C, "attention input must be dense NHWC");
-  CK(cam_pack_k(f.p, dt, (const float*)rnorm.p, kbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, c.stream));
+  SE_REQUIRE(!tc || (C % 32 == 0 && (C % 64 == 0 || C % 64 == 32)), "attention channel count");
+  CK(cam_pack_k(f.p, dt, (const float*)rnorm.p, kbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, ktc.r64, ktc.r32, c.stream));
 
   // ---- logits S[b, n, l] (fp32, row pitch Lpad), scaled by 10 * m_l in the GEMM epilogue
   Buf sbuf = c.get((size_t)B * L * Lpad * 4);
@@ -540,9 +555,8 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cw.CoutP = Lpad;
     cw.w_direct = (float*)kbuf.p;
     cw.has_tc = tc;
-    cw.tc.data = kbuf.p; cw.tc.ntaps = 16; cw.tc.nchunks = C / 32;
-    cw.tc.NT = 256; cw.tc.kch = tc_choose_kch(16 * (C / 32), 256); cw.tc.n_tiles = Lpad / 256; cw.tc.img_rows = 16 * (C / 32) * Lpad;
-    cw.tc.total_rows = (long long)B * cw.tc.img_rows;
+    cw.tc = ktc;
+    cw.tc.data = kbuf.p;
     cp.w_img_stride = (long long)16 * C * Lpad;
     CK(launch_conv(c, cp, cw, 2.0 * B * L * (double)L * C * 16));
   }
@@ -562,9 +576,13 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   c.put(colm);
 
   // ---- values + fold-sum
-  const size_t velems = (size_t)4 * B * 4 * Lpad * C;
-  Buf vbuf = c.get(velems * (tc ? 2 : 4));
-  CK(cam_pack_v(f.p, dt, vbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, c.stream));
+  TcWeights vtc;   // out = P V per sub-pixel class: 4 taps of Lpad "channels" (keys), N = C
+  vtc.ntaps = 4; vtc.n64 = Lpad / 64; vtc.n32 = 0; vtc.NT = (C + 15) / 16 * 16; vtc.n_tiles = 1;
+  tc_choose_stage(&vtc);
+  vtc.img_bytes = tc_weight_bytes_per_image(vtc);
+  const size_t per_pc_bytes = tc ? (size_t)B * vtc.img_bytes : (size_t)B * 4 * Lpad * C * 4;
+  Buf vbuf = c.get(4 * per_pc_bytes);
+  CK(cam_pack_v(f.p, dt, vbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, vtc.r64, (long long)per_pc_bytes, c.stream));
   for (int pc = 0; pc < 4; ++pc) {
     ConvParams cp;
     memset(&cp, 0, sizeof(cp));
@@ -578,14 +596,10 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     ClassW cw;
     cw.ntaps = 4;
     cw.CoutP = C;
-    const size_t per_pc = (size_t)B * 4 * Lpad * C;
-    cw.w_direct = (float*)vbuf.p + (tc ? 0 : pc * per_pc);
-    cw.has_tc = tc && (C % 16 == 0);
-    cw.tc.data = (const uint16_t*)vbuf.p + (tc ? pc * per_pc : 0);
-    cw.tc.ntaps = 4; cw.tc.nchunks = Lpad / 32; cw.tc.NT = C; cw.tc.n_tiles = 1;
-    cw.tc.kch = tc_choose_kch(4 * (Lpad / 32), C);
-    cw.tc.img_rows = 4 * (Lpad / 32) * C;
-    cw.tc.total_rows = (long long)B * cw.tc.img_rows;
+    cw.w_direct = reinterpret_cast<float*>((char*)vbuf.p + pc * per_pc_bytes);
+    cw.has_tc = tc;
+    cw.tc = vtc;
+    cw.tc.data = (const char*)vbuf.p + pc * per_pc_bytes;
     cp.w_img_stride = (long long)4 * Lpad * C;
     CK(launch_conv(c, cp, cw, 2.0 * B * (h / 2) * (w / 2) * (double)C * L * 4));
   }

@@ -3,6 +3,7 @@
 // conversion. All activations are NHWC; T is the activation storage type (bf16 fast path / fp32 exact).
 #include "se_common.cuh"
 #include "se_misc.h"
+#include "se_conv_tc.h"
 
 namespace se {
 
@@ -243,25 +244,35 @@ int cam_colmask(const float* mask_s, float* out, int B, int h, int w, int hs, in
 
 // ------------------------------------------------------------------------------------------ attention operands
 // Keys  K[l][(u,v,c)] = f[2ly+u, 2lx+v, c] * rnorm[c]        (splitcam.py:39-44, norm_type 1, 4x4 / stride 2)
-// tcgen05 layout: bf16 [b][tap=(u*4+v)][chunk=c/32][Lpad rows][32]
+// tcgen05 layout: per image, per 128-key tile, per stage the swizzled B image (se_conv_tc.h), 16 taps of C channels
 template <typename T>
-__global__ void cam_pack_k_tc_kernel(const T* __restrict__ f, const float* __restrict__ rnorm, __nv_bfloat16* __restrict__ out,
-                                     int B, int h, int w, int C, int ws, int L, int Lpad, long long total) {
+__global__ void cam_pack_k_tc_kernel(const T* __restrict__ f, const float* __restrict__ rnorm, uint8_t* __restrict__ out,
+                                     int B, int h, int w, int C, int ws, int L, int Lpad, int r64, int r32, long long total) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int k = (int)(i % 32);
-  long long r = i / 32;
+  const int c = (int)(i % C);
+  long long r = i / C;
   const int l = (int)(r % Lpad); r /= Lpad;
-  const int nch = C / 32;
-  const int chunk = (int)(r % nch); r /= nch;
   const int tap = (int)(r % 16);
   const long long b = r / 16;
   float v = 0.0f;
   if (l < L) {
-    const int ly = l / ws, lx = l % ws, u = tap / 4, vv = tap % 4, c = chunk * 32 + k;
+    const int ly = l / ws, lx = l % ws, u = tap / 4, vv = tap % 4;
     v = to_f<T>(f[((b * h + 2 * ly + u) * w + 2 * lx + vv) * C + c]) * rnorm[b * C + c];
   }
-  out[i] = __float2bfloat16(v);
+  const int NT = 128, n64 = C / 64, n32 = (C % 64) ? 1 : 0;
+  const int ksteps = n64 ? 16 * n64 / r64 : 16 / r32;
+  const int sb = NT * (r64 * 128 + r32 * 64);
+  const int nt = l / NT, n = l % NT;
+  int ks, j;
+  bool is64 = c < n64 * 64;
+  int k;
+  if (is64) { const int u = tap * n64 + c / 64; ks = u / r64; j = u % r64; k = c % 64; }
+  else { ks = tap / r32; j = tap % r32; k = c - n64 * 64; }
+  const size_t img_bytes = (size_t)(Lpad / NT) * ksteps * sb;
+  uint8_t* dst = out + (size_t)b * img_bytes + ((size_t)nt * ksteps + ks) * sb + tc_b_image_offset(NT, n64 ? r64 : 0, is64, j, n, k);
+  *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(v);
+  (void)n32;
 }
 
 // direct layout: fp32 [b][tap][c][CoutP]
@@ -284,11 +295,11 @@ __global__ void cam_pack_k_direct_kernel(const T* __restrict__ f, const float* _
 }
 
 int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L,
-               int Lpad, cudaStream_t s) {
+               int Lpad, int r64, int r32, cudaStream_t s) {
   const long long total = (long long)B * 16 * C * Lpad;
   if (tc_layout) {
-    SE_REQUIRE(C % 32 == 0, "C % 32");
-    SE_DISPATCH_T(dt, (cam_pack_k_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (__nv_bfloat16*)out, B, h, w, C, ws, L, Lpad, total)));
+    SE_REQUIRE(C % 32 == 0 && Lpad % 128 == 0, "C % 32, Lpad % 128");
+    SE_DISPATCH_T(dt, (cam_pack_k_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, r32, total)));
   } else {
     SE_DISPATCH_T(dt, (cam_pack_k_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (float*)out, B, h, w, C, ws, L, Lpad, total)));
   }
@@ -299,27 +310,29 @@ int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layo
 // Values for the fold-sum written as 4 sub-pixel (parity) 2x2 "convolutions" over the token image
 // P[b, ny, nx, l] (splitcam.py:152, utils.py:102-128):
 //   out[2yy+py, 2xx+px, c] = sum_{a,b in {0,1}} sum_l P[yy-a, xx-b, l] * f[2ly+py+2a, 2lx+px+2b, c]
-// tcgen05 layout: bf16 [pc][b][tap=(a*2+b)][chunk=l/32][C rows][32]
+// tcgen05 layout: per sub-pixel class pc, per image, per stage the swizzled B image: K = (tap, key l) in 64-wide
+// units, N = channel c
 template <typename T>
-__global__ void cam_pack_v_tc_kernel(const T* __restrict__ f, __nv_bfloat16* __restrict__ out, int B, int h, int w, int C, int ws,
-                                     int L, int Lpad, long long total) {
+__global__ void cam_pack_v_tc_kernel(const T* __restrict__ f, uint8_t* __restrict__ out, int B, int h, int w, int C, int ws,
+                                     int L, int Lpad, int r64, long long pc_bytes, long long total) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int k = (int)(i % 32);
-  long long r = i / 32;
-  const int c = (int)(r % C); r /= C;
-  const int nch = Lpad / 32;
-  const int chunk = (int)(r % nch); r /= nch;
+  const int c = (int)(i % C);
+  long long r = i / C;
+  const int l = (int)(r % Lpad); r /= Lpad;
   const int tap = (int)(r % 4); r /= 4;
   const long long b = r % B;
   const int pc = (int)(r / B);
-  const int l = chunk * 32 + k;
   float v = 0.0f;
   if (l < L) {
     const int ly = l / ws, lx = l % ws, py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
     v = to_f<T>(f[((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + c]);
   }
-  out[i] = __float2bfloat16(v);
+  const int NT = (C + 15) / 16 * 16, n64 = Lpad / 64;
+  const int ksteps = 4 * n64 / r64, sb = NT * r64 * 128;
+  const int u = tap * n64 + l / 64, ks = u / r64, j = u % r64;
+  uint8_t* dst = out + (size_t)pc * pc_bytes + (size_t)b * ((size_t)ksteps * sb) + (size_t)ks * sb + tc_b_image_offset(NT, r64, true, j, c, l % 64);
+  *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(v);
 }
 
 // direct layout: fp32 [pc][b][tap][l (Ci = Lpad)][CoutP = C]
@@ -342,11 +355,13 @@ __global__ void cam_pack_v_direct_kernel(const T* __restrict__ f, float* __restr
   out[i] = v;
 }
 
-int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L, int Lpad, cudaStream_t s) {
+int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L, int Lpad, int r64,
+               long long pc_bytes, cudaStream_t s) {
   const long long total = 4LL * B * 4 * Lpad * C;
   if (tc_layout) {
-    SE_REQUIRE(Lpad % 32 == 0, "Lpad % 32");
-    SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (__nv_bfloat16*)out, B, h, w, C, ws, L, Lpad, total)));
+    SE_REQUIRE(Lpad % 64 == 0, "Lpad % 64");
+    if (C % 16) SE_CUDA_OK(cudaMemsetAsync(out, 0, 4 * pc_bytes, s));   // padded N rows
+    SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes, total)));
   } else {
     SE_DISPATCH_T(dt, (cam_pack_v_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (float*)out, B, h, w, C, ws, L, Lpad, total)));
   }
