@@ -195,10 +195,12 @@ def run_b200(args):
     img_d, sk_d = img_h.cuda(non_blocking=True), sk_h.cuda(non_blocking=True)
     gathered = torch.empty(world * B, 4, H, W, device="cuda") if world > 1 else None
 
+    from sketchedit_b200 import parallel
+
     def step_device():
         composed, mask, _ = eng.inference(img_d, sk_d, precision=prec)
         if world > 1:   # the path's single collective: all-gather of the packed output tiles over NVLink
-            dist.all_gather_into_tensor(gathered, torch.cat([composed, mask], 1))
+            parallel.all_gather_outputs(composed, mask, out=gathered)
         return composed, mask
 
     def barrier():

@@ -57,8 +57,10 @@ enum DType : int { DT_BF16 = 0, DT_F32 = 1 };
 // offset choff. Weights may differ per image (attention), w_img_stride = 0 otherwise.
 struct ConvParams {
   // input
-  const void* x;        // NHWC, dtype in_dt, pixel pitch ldx elements
+  const void* x;        // NHWC, dtype in_dt, pixel pitch ldx elements (or C8, see in_c8)
   int in_dt;
+  int in_c8;            // 1: input is C8 = [N][ldx blocks][Hi][Wi][8] starting at channel block x_cb_off (se_conv_c8.cu only)
+  int x_cb_off;
   int N, Hi, Wi, Ci, ldx;
   long long x_row_pitch, x_img_pitch;   // elements; 0 = dense (Wi*ldx, Hi*Wi*ldx). ldx may be < Ci (overlapping windows)
   // position grid + taps
@@ -73,12 +75,26 @@ struct ConvParams {
   // output
   void* y;
   int out_dt;
+  int out_c8;           // 0: NHWC (pitch ldo, channel offset choff); 1: C8 = [N][ldo blocks][H][W][8], choff % 8 == 0 (bf16 only)
   int Hout, Wout, ldo, choff;
   int osy, ooy, osx, oox;
   // epilogue
   int epi;
   float scale;                  // EPI_LINEAR
   const float* colscale;        // EPI_LINEAR: [N][Cout] or nullptr
+};
+
+// Output side of one launch (shared by both kernels). Layouts: NHWC (pixel pitch ldo elements, channel offset
+// choff) or C8 = [N][CBtot][H][W][8] (ldo = CBtot channel blocks, choff multiple of 8).
+struct EpiParams {
+  void* y;
+  int out_dt, out_c8;
+  int Hout, Wout, ldo, choff;
+  int osy, ooy, osx, oox;
+  int epi;
+  float scale;
+  const float* colscale;
+  int Cout, NT;
 };
 
 // ------------------------------------------------------------------------------------------

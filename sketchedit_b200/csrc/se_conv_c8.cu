@@ -1,0 +1,492 @@
+// tcgen05 implicit-GEMM convolution over CHANNEL-BLOCKED activations ("C8": [N][C/8][H][W][8] bf16) for sm_100a.
+//
+// Why this layout: 8 horizontally adjacent pixels of one channel block are 128 contiguous bytes = exactly one UMMA
+// "core matrix" (8 rows x 16 B) of the no-swizzle K-major operand layout. So a spatial region of the input landed
+// in shared memory by ONE TMA box [blocks][rows][cols*8] is directly usable as the A operand of EVERY tap of the
+// convolution: the tap only changes the descriptor's start address (LBO = block plane size, SBO = row pitch).
+//   * stride-1 convs with dilation <= 2 and the four sub-pixel classes of the x2 deconvs: the (16+2p) x (8+2p) halo
+//     of a 16 x 8 output tile is loaded once per tile (double buffered) and re-used by all taps  ("HALO" mode;
+//     A traffic drops from taps x tile to ~1.4 x tile, TMA row requests by >10x)
+//   * dilation >= 4: one box per tap                                                           ("PERTAP" mode)
+//   * 5x5 stems over the 8-channel packed input: GEMM-K runs over the pixel window (LBO = 16 B): 5 taps x 3 MMAs.
+// The B operand (weights) is the pre-swizzled stage image of se_conv_tc.h, either streamed per k-step with
+// cp.async.bulk or, when the whole layer fits (<= ~112 KB), loaded once and kept resident in shared memory.
+// Warp roles, TMEM double buffering and the fused epilogue are those of se_conv_tc.cu.
+#include "se_conv_c8.h"
+
+#include <stdlib.h>
+
+#include <vector>
+
+#include "se_tc_device.cuh"
+
+namespace se {
+
+constexpr int C8_TH = 16, C8_TW = 8;   // output tile: 16 rows x 8 columns = 128 positions
+
+// no-swizzle K-major operand: core matrices of 8 rows x 16 B; LBO = next core matrix along K, SBO = along M
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version 1 (sm_100); layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, bool sw128) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((sw128 ? 1024 : 512) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(sw128 ? 2 : 4) << 61;
+  return d;
+}
+
+// R64 / R32 / MMAS: compile-time copies of p.r64 / p.r32 / p.mmas64 (R64 < 0: take them from p at run time).
+// With compile-time trip counts the MMA issue sequence of a k-step is fully unrolled, so descriptor arithmetic of
+// later MMAs overlaps the (long) issue latency of earlier ones: tools/bench/mma_rate.cu measures ~110 cycles per
+// MMA for a rolled loop against the 40-96 cycle pipe time, i.e. a rolled loop starves the tensor core.
+template <int R64, int R32, int MMAS>
+__global__ void __launch_bounds__(TC_NUM_THREADS, 1)
+conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
+  const int r64 = R64 >= 0 ? R64 : p.r64, r32 = R64 >= 0 ? R32 : p.r32, mmas64 = R64 >= 0 ? MMAS : p.mmas64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // carve: [halo A buffers][resident weights][stages: (tap A box) + (B image)] [barriers][tmem ptr][bias]
+  const bool halo = (p.mode == C8_HALO);
+  const int b64_bytes = p.NT * 128, b32_bytes = p.NT * 64;
+  const int b_bytes = r64 * b64_bytes + r32 * b32_bytes;
+  const int stage_a = halo ? 0 : p.a_bytes;
+  const int stage_b = p.resident ? 0 : b_bytes;
+  const int stage_bytes = stage_a + stage_b;
+  uint8_t* sHalo = smem;
+  uint8_t* sWres = sHalo + (halo ? p.a_bufs * p.a_bytes : 0);
+  uint8_t* sStages = sWres + (p.resident ? p.wres_bytes : 0);
+  uint8_t* tail = sStages + (size_t)p.num_stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+  uint64_t* a_full = empty_bar + TC_MAX_STAGES;
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* tmem_full = a_empty + 2;
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint64_t* wres_bar = tmem_empty + 4;
+  // accumulator ring: N <= 128 leaves room for 4 TMEM stages; the two epilogue groups then drain alternate tiles
+  // (each group gets twice the time per tile); wider tiles keep 2 stages and split a tile's columns between groups
+  const int acc_stages = p.NT <= 128 ? 4 : 2;
+  const int acc_stride = p.NT <= 128 ? 128 : 256;
+  const int epi_split = acc_stages == 4 ? 1 : TC_EPI_GROUPS;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(wres_bar + 1);
+  float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 16 B aligned: read with ld.shared.v4
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC_MAX_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128 * epi_split);
+    }
+    mbar_init(wres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const int cst_n = p.NT + 32;
+  epi_fill_constants(bias_s, cst_n, p.bias, p.e.Cout, threadIdx.x, TC_NUM_THREADS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_tiles = p.N * p.tiles_x * p.tiles_y;
+  const int ksteps = p.ksteps;
+  const bool staged = stage_bytes > 0;
+
+  if (warp == 0) {
+    // ==================================================================== producer
+    if (p.resident && elect_one()) {
+      // whole layer's weights, once: bulk copies of <= 64 KB
+      mbar_expect_tx(wres_bar, (uint32_t)p.wres_bytes);
+      for (int off = 0; off < p.wres_bytes; off += 65536) {
+        const int n = min(65536, p.wres_bytes - off);
+        bulk_load_1d(sWres + off, p.w + off, (uint32_t)n, wres_bar);
+      }
+    }
+    __syncwarp();
+    int stage = 0, iter = 0;
+    uint32_t phase = 0;
+    long long t_wait = 0, t_begin = clock64();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      int rest = tile;
+      const int tx = rest % p.tiles_x;
+      rest /= p.tiles_x;
+      const int ty = rest % p.tiles_y;
+      const int img = rest / p.tiles_y;
+      const int x0 = tx * C8_TW, y0 = ty * C8_TH;
+      if (halo) {
+        const int ab = (p.a_bufs == 2) ? (iter & 1) : 0;               // no integer division: keeps the value uniform
+        const uint32_t aphase = (p.a_bufs == 2) ? ((iter >> 1) & 1) : (iter & 1);
+        const long long tw = p.dbg ? clock64() : 0;
+        mbar_wait(&a_empty[ab], aphase ^ 1, 5);
+        if (p.dbg) t_wait += clock64() - tw;
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[ab], (uint32_t)p.a_tx_bytes);
+          tma_load_4d(sHalo + (size_t)ab * p.a_bytes, &tmA, &a_full[ab], (x0 - p.pad_x0) * 8, y0 - p.pad_y0, p.x_cb_off, img);
+        }
+        __syncwarp();
+      }
+      if (staged) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const long long tw = p.dbg ? clock64() : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          if (p.dbg) t_wait += clock64() - tw;
+          uint8_t* st = sStages + (size_t)stage * stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
+            if (!p.resident) bulk_load_1d(st + stage_a, p.w + (size_t)ks * b_bytes, (uint32_t)b_bytes, &full_bar[stage]);
+            if (!halo) {   // PERTAP: a stage is exactly one tap
+              tma_load_4d(st, &tmA, &full_bar[stage], (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off, img);
+            }
+          }
+          __syncwarp();
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
+  } else if (warp == 1) {
+    // ==================================================================== MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0, iter = 0;
+    uint32_t phase = 0;
+    long long t_wfull = 0, t_wtmem = 0, t_begin = clock64();
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t off_wres = halo ? (uint32_t)(p.a_bufs * p.a_bytes) : 0u;
+    const uint32_t off_stages = off_wres + (p.resident ? (uint32_t)p.wres_bytes : 0u);
+    if (p.resident) mbar_wait(wres_bar, 0, 6);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & (acc_stages - 1);
+      const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
+      long long tw = p.dbg ? clock64() : 0;
+      mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
+      if (p.dbg) t_wtmem += clock64() - tw;
+      const int ab = (halo && p.a_bufs == 2) ? (iter & 1) : 0;
+      if (halo) {
+        tw = p.dbg ? clock64() : 0;
+        mbar_wait(&a_full[ab], (p.a_bufs == 2) ? ((iter >> 1) & 1) : (iter & 1), 7);
+        if (p.dbg) t_wfull += clock64() - tw;
+      }
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * acc_stride;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        if (staged) {
+          tw = p.dbg ? clock64() : 0;
+          mbar_wait(&full_bar[stage], phase, 3);
+          if (p.dbg) t_wfull += clock64() - tw;
+          tc_fence_after();
+        }
+        // shared-window addresses as plain 32-bit integer arithmetic on the (constant) window base: stays uniform
+        const uint32_t st = smem_base + off_stages + (uint32_t)stage * stage_bytes;
+        const uint32_t sB = p.resident ? smem_base + off_wres + (uint32_t)ks * b_bytes : st + stage_a;
+        const uint32_t sA = halo ? smem_base + (uint32_t)ab * p.a_bytes : st;
+        {
+          const uint32_t lead = elect_one() ? 1u : 0u;   // predicate only: no divergent region around the issue loop
+          uint32_t acc = ks ? 1u : 0u;
+          // descriptors: only the 14-bit start-address field (bytes >> 4) changes between MMAs
+          const uint32_t a_lo = ((p.lbo_bytes >> 4) & 0x3FFF) << 16;
+          const uint32_t a_hi = ((p.sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
+          const uint32_t b_hi128 = (1024u >> 4) | (1u << 14) | (2u << 29), b_hi64 = (512u >> 4) | (1u << 14) | (4u << 29);
+          const uint32_t kstep16 = p.kstep_bytes >> 4;
+          const uint32_t n_u64 = p.ntaps * p.n64;
+          // A offsets come from the constant bank (compile-time indices when the k-step structure is templated)
+          const int u0 = ks * r64, v0 = n_u64 + ks * r32;
+#pragma unroll
+          for (int j = 0; j < (R64 >= 0 ? R64 : 32); ++j) {
+            if (j < r64) {
+              const uint32_t a0 = (sA + p.aoff[u0 + j]) >> 4;
+              const uint32_t b0 = (sB + j * b64_bytes) >> 4;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < mmas64) {
+                  umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+                  acc = 1u;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < (R64 >= 0 ? R32 : 32); ++j) {
+            if (j < r32) {
+              const uint32_t a0 = (sA + p.aoff[v0 + j]) >> 4;
+              const uint32_t b0 = (sB + r64 * b64_bytes + j * b32_bytes) >> 4;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
+                acc = 1u;
+              }
+            }
+          }
+          if (staged) umma_commit_if(lead, &empty_bar[stage]);
+          if (ks == ksteps - 1) {
+            if (halo) umma_commit_if(lead, &a_empty[ab]);
+            umma_commit_if(lead, &tmem_full[as]);
+          }
+        }
+        __syncwarp();
+        if (staged && ++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
+  } else if (warp >= 4) {
+    // ==================================================================== epilogue
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int ry = row / C8_TW, rx = row % C8_TW;
+    int iter = 0;
+    long long t_wacc = 0, t_begin = clock64();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      int rest = tile;
+      const int tx = rest % p.tiles_x;
+      rest /= p.tiles_x;
+      const int ty = rest % p.tiles_y;
+      const int img = rest / p.tiles_y;
+      if (epi_split == 1 && (iter & 1) != grp) continue;      // tile-alternating groups
+      const int as = iter & (acc_stages - 1);
+      const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
+      const long long tw = p.dbg ? clock64() : 0;
+      mbar_wait(&tmem_full[as], accphase, 4);
+      if (p.dbg) t_wacc += clock64() - tw;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_stride;
+      const int py = ty * C8_TH + ry, px = tx * C8_TW + rx;
+      const bool valid = (py < p.Ho) && (px < p.Wo);
+      tc_epilogue_tile(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+    if (p.dbg && threadIdx.x == 128) { p.dbg[blockIdx.x * 8 + 5] = t_wacc; p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin; }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn c8_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int g_sms = 0, g_optin = 0;
+static const int kSmemBudget = 200 * 1024;
+static const int kResidentMax = 112 * 1024;
+
+// geometry shared by the weight packer (stage grouping) and the launcher
+int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem) {
+  L->stem = stem;
+  int mn_y = 0, mx_y = 0, mn_x = 0, mx_x = 0;
+  for (int t = 0; t < ntaps; ++t) {
+    mn_y = dy[t] < mn_y ? dy[t] : mn_y; mx_y = dy[t] > mx_y ? dy[t] : mx_y;
+    mn_x = dx[t] < mn_x ? dx[t] : mn_x; mx_x = dx[t] > mx_x ? dx[t] : mx_x;
+  }
+  const int extra_x = stem ? 5 : 0;   // the stem's GEMM-K walks 6 pixels to the right of the tap origin
+  const int HR = C8_TH + (mx_y - mn_y), WR = C8_TW + (mx_x - mn_x) + extra_x;
+  TcWeights& w = L->w;
+  w.ntaps = ntaps;
+  if (stem) { w.n64 = 1; w.n32 = 0; }
+  else {
+    w.n64 = Ci / 64;
+    int rem = Ci - 64 * w.n64;
+    if (rem > 32) { ++w.n64; rem = 0; }
+    w.n32 = rem > 0 ? 1 : 0;
+  }
+  // the box covers the zero-padded GEMM K (whole 64 / 32 channel chunks): blocks past the tensor are TMA zero fill,
+  // so the MMAs never multiply stale shared memory (possibly NaN bit patterns) by the zero weight columns
+  L->cb_in = stem ? 1 : (w.n64 * 64 + w.n32 * 32) / 8;
+  const long long halo_bytes = (long long)L->cb_in * HR * WR * 16;
+  w.NT = (Cout + 15) / 16 * 16;
+  w.n_tiles = 1;
+  w.img_bytes = 0;
+  const long long wbytes = (long long)ntaps * w.NT * (w.n64 * 128 + w.n32 * 64);
+  // halo re-use while the region stays small enough to sit next to the weight stages (one or two buffers,
+  // decided at launch); larger dilations fetch one box per tap
+  L->mode = (halo_bytes <= 72 * 1024) ? C8_HALO : C8_PERTAP;
+  if (L->mode == C8_HALO) {
+    L->HR = HR; L->WR = WR; L->pad_y0 = -mn_y; L->pad_x0 = -mn_x;
+  } else {
+    L->HR = C8_TH; L->WR = C8_TW; L->pad_y0 = 0; L->pad_x0 = 0;
+  }
+  L->a_tx_bytes = L->cb_in * L->HR * L->WR * 16;
+  L->a_bytes = (L->a_tx_bytes + 1023) / 1024 * 1024;
+  L->resident = (wbytes <= kResidentMax) && (2 * L->a_bytes + wbytes <= kSmemBudget);
+  // stage grouping: PERTAP -> one tap per stage; otherwise B-only stages of <= 48 KB (whole taps for mixed chunking)
+  if (L->resident && L->mode == C8_HALO) {
+    // nothing is streamed per k-step: one k-step issues every MMA of the tile back to back
+    w.r64 = ntaps * w.n64;
+    w.r32 = ntaps * w.n32;
+  } else if (L->mode == C8_PERTAP || (w.n64 > 0 && w.n32 > 0)) { w.r64 = w.n64; w.r32 = w.n32; }
+  else {
+    const int unit = w.n64 ? w.NT * 128 : w.NT * 64, total = ntaps * (w.n64 ? w.n64 : w.n32);
+    int best = 1;
+    for (int k = 1; k <= 8 && k <= total; ++k)
+      if (total % k == 0 && k * unit <= 48 * 1024) best = k;
+    if (w.n64) { w.r64 = best; w.r32 = 0; } else { w.r64 = 0; w.r32 = best; }
+  }
+  if (L->mode == C8_PERTAP) SE_REQUIRE(tc_ksteps(w) == ntaps, "per-tap stages must be whole taps");
+  return 0;
+}
+
+// the k-step structures of the generator's layers get their own fully unrolled instantiation
+#define C8_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(1, 0, 4) X(1, 1, 4) X(4, 4, 4) X(4, 0, 4) X(0, 3, 4) X(0, 1, 4)
+static int c8_set_smem_attr(int bytes) {
+#define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  C8_SPECIALISATIONS(X)
+#undef X
+  SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<-1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+static void c8_dispatch(const C8Params& p, const CUtensorMap& tmA, int grid, int smem_bytes, cudaStream_t stream) {
+#define X(a, b, m)                                                                             \
+  if (p.r64 == a && p.r32 == b && (a == 0 || p.mmas64 == m)) {                                 \
+    conv_c8_kernel<a, b, m><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, p);             \
+    return;                                                                                    \
+  }
+  C8_SPECIALISATIONS(X)
+#undef X
+  conv_c8_kernel<-1, 0, 0><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, p);
+}
+
+int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
+  const TcWeights& w = L.w;
+  SE_REQUIRE(c.in_dt == DT_BF16 && c.in_c8 == 1, "conv_c8 reads bf16 channel-blocked activations");
+  SE_REQUIRE(c.stride == 1, "conv_c8 handles stride-1 convolutions");
+  SE_REQUIRE((reinterpret_cast<uintptr_t>(c.x) & 127) == 0, "input base must be 128 B aligned");
+  SE_REQUIRE(c.ntaps == w.ntaps && c.ntaps <= MAX_TAPS, "tap count mismatch");
+  SE_REQUIRE(c.Wi * 8 <= (1 << 30) && L.WR * 8 <= 256 && L.HR <= 256 && L.cb_in <= 256, "TMA box limits");
+  C8Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = c.N; p.Ho = c.Ho; p.Wo = c.Wo;
+  p.tiles_x = (c.Wo + C8_TW - 1) / C8_TW;
+  p.tiles_y = (c.Ho + C8_TH - 1) / C8_TH;
+  p.ntaps = c.ntaps;
+  memcpy(p.dy, c.dy, sizeof(p.dy));
+  memcpy(p.dx, c.dx, sizeof(p.dx));
+  p.n64 = w.n64; p.n32 = w.n32; p.r64 = w.n64 ? w.r64 : 0; p.r32 = w.n32 ? w.r32 : 0; p.NT = w.NT;
+  p.ksteps = tc_ksteps(w);
+  p.w = reinterpret_cast<const uint8_t*>(w.data);
+  p.mode = L.mode; p.HR = L.HR; p.WR = L.WR; p.pad_y0 = L.pad_y0; p.pad_x0 = L.pad_x0;
+  p.cb_in = L.cb_in; p.x_cb_off = c.x_cb_off;
+  p.a_bytes = L.a_bytes; p.a_tx_bytes = L.a_tx_bytes;
+  p.resident = L.resident ? 1 : 0;
+  p.wres_bytes = (int)tc_weight_bytes_per_image(w);
+  if (L.stem) { p.lbo_bytes = 16; p.kstep_bytes = 32; p.mmas64 = 3; }
+  else { p.lbo_bytes = L.HR * L.WR * 16; p.kstep_bytes = 2 * p.lbo_bytes; p.mmas64 = 4; }
+  p.sbo_bytes = L.WR * 16;
+  p.bias = c.bias;
+  fill_epi(c, w.NT, &p.e);
+  {
+    // A-operand byte offsets inside the shared-memory region, per K unit (tile independent):
+    // 64-wide units first (u = tap*n64 + chunk), then the 32-wide unit of each tap
+    const bool halo = (L.mode == C8_HALO);
+    const int n_u64 = c.ntaps * w.n64, n_u32 = c.ntaps * w.n32;
+    SE_REQUIRE(n_u64 + n_u32 < C8_MAX_UNITS, "too many K units");
+    for (int u = 0; u < n_u64 + n_u32; ++u) {
+      const bool is64 = u < n_u64;
+      const int t = is64 ? u / w.n64 : u - n_u64;
+      const int cb0 = is64 ? (u - t * w.n64) * 8 : w.n64 * 8;
+      const int oy = halo ? c.dy[t] + L.pad_y0 : 0, ox = halo ? c.dx[t] + L.pad_x0 : 0;
+      p.aoff[u] = (uint32_t)((cb0 * L.HR + oy) * L.WR + ox) * 16u;
+    }
+  }
+  SE_REQUIRE(c.epi == EPI_LINEAR || (c.Cout % 2 == 0 && c.out_dt == DT_BF16), "gated epilogue needs even Cout, bf16 out");
+  SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
+
+  const int b_bytes = tc_stage_b_bytes(w);
+  const int stage_bytes = (L.mode == C8_HALO ? 0 : L.a_bytes) + (L.resident ? 0 : b_bytes);
+  int fixed = (L.resident ? p.wres_bytes : 0);
+  p.a_bufs = 2;
+  if (L.mode == C8_HALO) {
+    if (fixed + 2 * L.a_bytes + 3 * stage_bytes > kSmemBudget) p.a_bufs = 1;   // measured: 2 halo buffers + 3 weight stages beats 1 + 4
+    fixed += p.a_bufs * L.a_bytes;
+  }
+  int stages = stage_bytes ? (kSmemBudget - fixed) / stage_bytes : 1;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  SE_REQUIRE(stages >= (stage_bytes ? 2 : 1), "shared memory plan does not fit");
+  p.num_stages = stages;
+  const int smem_bytes = 1024 + fixed + stages * stage_bytes + (2 * TC_MAX_STAGES + 13) * 8 + 16 + 3 * (p.NT + 32) * 4 + 64;
+
+  EncodeTiledFn enc = c8_encode_fn();
+  SE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  if (!g_sms) {
+    int dev = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    SE_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    SE_CUDA_OK(cudaDeviceGetAttribute(&g_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    { int rc_attr = c8_set_smem_attr(g_optin); if (rc_attr) return rc_attr; }
+  }
+  SE_REQUIRE(smem_bytes <= g_optin, "shared memory plan exceeds the opt-in limit");
+
+  CUtensorMap tmA;
+  {
+    // C8 activations viewed as (8*W, H, CB, N): a row of the box is WR pixels x 16 B, contiguous in memory
+    cuuint64_t dims[4] = {(cuuint64_t)c.Wi * 8, (cuuint64_t)c.Hi, (cuuint64_t)c.ldx, (cuuint64_t)c.N};
+    cuuint64_t strides[3] = {(cuuint64_t)c.Wi * 16, (cuuint64_t)c.Hi * c.Wi * 16, (cuuint64_t)c.ldx * c.Hi * c.Wi * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(L.WR * 8), (cuuint32_t)L.HR, (cuuint32_t)L.cb_in, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(C8) failed, CUresult=" + std::to_string((int)r));
+  }
+  const int total_tiles = p.N * p.tiles_x * p.tiles_y;
+  const int grid = total_tiles < g_sms ? total_tiles : g_sms;
+  static const bool dbg_on = getenv("SE_TC_DEBUG") != nullptr;
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) SE_CUDA_OK(cudaMalloc(&dbg_buf, 8 * 8 * 1024));
+    SE_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 8 * 8 * 1024, stream));
+    p.dbg = dbg_buf;
+  }
+  c8_dispatch(p, tmA, grid, smem_bytes, stream);
+  SE_CUDA_OK(cudaGetLastError());
+  if (dbg_on) {
+    SE_CUDA_OK(cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> h(8 * grid);
+    SE_CUDA_OK(cudaMemcpy(h.data(), dbg_buf, h.size() * 8, cudaMemcpyDeviceToHost));
+    double a[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 8 + k] / grid;
+    fprintf(stderr,
+            "[c8] N=%d %dx%d Ci=%d taps=%d NT=%d mode=%s res=%d HRxWR=%dx%d abufs=%d n64=%d n32=%d r64=%d r32=%d stages=%d tiles=%d | prod wait %.0f/%.0f | mma wait_full %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f\n",
+            c.N, c.Ho, c.Wo, c.Ci, c.ntaps, p.NT, L.mode == C8_HALO ? "halo" : "pertap", p.resident, L.HR, L.WR, p.a_bufs, p.n64, p.n32, p.r64, p.r32,
+            p.num_stages, total_tiles, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+  }
+  return 0;
+}
+
+}  // namespace se

@@ -1,0 +1,43 @@
+// Host/device interface of the channel-blocked tcgen05 convolution (se_conv_c8.cu).
+#pragma once
+#include "se_common.cuh"
+#include "se_conv_tc.h"
+
+namespace se {
+
+enum { C8_HALO = 0, C8_PERTAP = 1 };
+constexpr int C8_MAX_UNITS = 64;   // (tap, channel chunk) K units per tile
+
+// per-layer (per sub-pixel class) configuration fixed at weight-packing time
+struct C8Layer {
+  TcWeights w;          // B stage images (se_conv_tc.h), n_tiles = 1, shared weights
+  int mode = C8_HALO;
+  bool resident = false;
+  bool stem = false;    // GEMM-K walks the pixel window of the 8-channel packed input
+  int cb_in = 0;        // channel blocks read
+  int HR = 0, WR = 0;   // rows / columns of the shared-memory A region
+  int pad_y0 = 0, pad_x0 = 0;
+  int a_bytes = 0, a_tx_bytes = 0;
+};
+
+struct C8Params {
+  int N, Ho, Wo;
+  int tiles_x, tiles_y;
+  int ntaps;
+  int8_t dy[MAX_TAPS], dx[MAX_TAPS];
+  int n64, n32, r64, r32, NT, ksteps;
+  const uint8_t* w;
+  int mode, HR, WR, pad_y0, pad_x0, cb_in, x_cb_off;
+  int a_bytes, a_tx_bytes, a_bufs;
+  int lbo_bytes, sbo_bytes, kstep_bytes, mmas64;
+  uint32_t aoff[C8_MAX_UNITS];   // byte offset of each K unit's A operand inside the shared-memory region
+  int num_stages, resident, wres_bytes;
+  const float* bias;
+  EpiParams e;
+  unsigned long long* dbg;
+};
+
+int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem);
+int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream);
+
+}  // namespace se

@@ -14,133 +14,13 @@
 //   warp 2 : TMEM allocator                 warps 4-7 : epilogue (TMEM lane quadrant = warp % 4)
 #include "se_common.cuh"
 #include "se_conv_tc.h"
+#include "se_tc_device.cuh"
 
 #include <stdlib.h>
 
 #include <vector>
 
 namespace se {
-
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded spin: a protocol bug traps instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  printf("se_conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-  __trap();
-}
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-// linear global -> shared bulk copy (bytes % 16 == 0), completion on an mbarrier
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// one lane of a fully converged warp (the warp stays converged: the compiler keeps addresses / descriptors
-// in uniform registers instead of broadcasting them lane by lane)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives once all previously issued MMAs of this thread have completed.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// must be executed before the registers written by tmem_ld16 are read
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// write cnt (<= 16) consecutive channels of one pixel; static register indexing only (no local memory)
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* o, const float (&r)[16], int cnt, bool al8, bool al4) {
-  if (cnt == 16 && al8) {
-    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
-    *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15]));
-  } else if (al4) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (4 * j + 4 <= cnt) *reinterpret_cast<uint2*>(o + 4 * j) = make_uint2(pack_bf16x2(r[4 * j], r[4 * j + 1]), pack_bf16x2(r[4 * j + 2], r[4 * j + 3]));
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i >= (cnt & ~3) && i < cnt) o[i] = __float2bfloat16(r[i]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < cnt) o[i] = __float2bfloat16(r[i]);
-  }
-}
-__device__ __forceinline__ void store_row_f32(float* o, const float (&r)[16], int cnt, bool al4) {
-  if (cnt == 16 && al4) {
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < cnt) o[i] = r[i];
-  }
-}
 
 // K-major operand tiles (cute::UMMA::SmemDescriptor): rows of 128 B (SWIZZLE_128B, 8-row atoms 1024 B apart)
 // or rows of 64 B (SWIZZLE_64B, atoms 512 B apart). Only the 14-bit start-address field changes per MMA.
@@ -156,10 +36,10 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, bool sw
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int A64_BYTES = TILE_M * 128;              // 64-channel A unit
 constexpr int A32_BYTES = TILE_M * 64;               // 32-channel A unit
-constexpr int NUM_THREADS = 256;
-constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;                      // TMEM columns between the two accumulator stages
-constexpr int MAX_STAGES = 8;
+constexpr int NUM_THREADS = TC_NUM_THREADS;
+constexpr int TMEM_COLS = TC_TMEM_COLS;
+constexpr int ACC_STRIDE = TC_ACC_STRIDE;
+constexpr int MAX_STAGES = TC_MAX_STAGES;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmA32, const TcParams p) {
@@ -176,7 +56,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 16 B aligned: read with ld.shared.v4
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,7 +72,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], TC_EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -201,7 +81,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // bias (all N tiles) into shared memory; zero when absent
-  for (int i = threadIdx.x; i < p.n_tiles * p.NT + 32; i += NUM_THREADS) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.0f;
+  const int cst_n = p.n_tiles * p.NT + 32;
+  epi_fill_constants(bias_s, cst_n, p.bias, p.e.Cout, threadIdx.x, NUM_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -226,9 +107,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
       const int x0 = tx * TILE_W * p.stride, y0 = ty * TILE_H * p.stride;
       const uint8_t* wsrc = p.w + (size_t)img * p.w_img_bytes + (size_t)nt * ksteps * b_bytes;
       for (int ks = 0; ks < ksteps; ++ks) {
-        const long long tw = clock64();
+        const long long tw = p.dbg ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-        t_wait += clock64() - tw;
+        if (p.dbg) t_wait += clock64() - tw;
         uint8_t* sA = smem + (size_t)stage * stage_bytes;
         if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
@@ -259,15 +140,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      long long tw = clock64();
+      long long tw = p.dbg ? clock64() : 0;
       mbar_wait(&tmem_empty[as], aphase ^ 1, 2);
-      t_wtmem += clock64() - tw;
+      if (p.dbg) t_wtmem += clock64() - tw;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
       for (int ks = 0; ks < ksteps; ++ks) {
-        tw = clock64();
+        tw = p.dbg ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase, 3);
-        t_wfull += clock64() - tw;
+        if (p.dbg) t_wfull += clock64() - tw;
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t sB = sA + a_bytes;
@@ -305,6 +186,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
   } else if (warp >= 4) {
     // ==================================================================== epilogue
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int grp = (warp - 4) >> 2;            // which share of the 16-column chunks this warp drains
     const int row = q * 32 + lane;             // tile row == TMEM lane == output position in tile
     const int ry = row / TILE_W, rx = row % TILE_W;
     int iter = 0;
@@ -318,61 +200,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
       const int img = rest / p.tiles_y;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      const long long tw = clock64();
+      const long long tw = p.dbg ? clock64() : 0;
       mbar_wait(&tmem_full[as], aphase, 4);
-      t_wacc += clock64() - tw;
+      if (p.dbg) t_wacc += clock64() - tw;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
       const int py = ty * TILE_H + ry, px = tx * TILE_W + rx;
       const bool valid = (py < p.Ho) && (px < p.Wo);
-      const int oy = py * p.osy + p.ooy, ox = px * p.osx + p.oox;
-      const size_t opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
-
-      if (p.epi == EPI_LINEAR) {
-        const int n0 = nt * p.NT;
-        const float* cs = p.colscale ? p.colscale + (size_t)img * p.Cout : nullptr;
-        const bool al4 = ((p.ldo | p.choff) & 3) == 0, al8 = ((p.ldo | p.choff) & 7) == 0;
-        for (int c0 = 0; c0 < p.NT; c0 += 16) {
-          const int cb = n0 + c0;
-          if (cb >= p.Cout) break;
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (valid) {
-            const int cnt = min(16, p.Cout - cb);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float sc = p.scale;
-              if (cs != nullptr && i < cnt) sc *= __ldg(cs + cb + i);
-              v[i] = (v[i] + bias_s[cb + i]) * sc;
-            }
-            if (p.out_dt == DT_F32) store_row_f32(reinterpret_cast<float*>(p.y) + opix * p.ldo + p.choff + cb, v, cnt, al4);
-            else store_row_bf16(reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.ldo + p.choff + cb, v, cnt, al8, al4);
-          }
-        }
-      } else {
-        // gated: feature column c pairs with gate column c + half; both live in this thread's lane
-        const int half = p.Cout >> 1;
-        const bool is_elu = (p.epi == EPI_GATE_ELU);
-        const bool al4 = ((p.ldo | p.choff) & 3) == 0, al8 = ((p.ldo | p.choff) & 7) == 0;
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.ldo + p.choff;
-        for (int c0 = 0; c0 < half; c0 += 16) {
-          float f[16], g[16];
-          tmem_ld16(taddr + c0, f);
-          tmem_ld16(taddr + half + c0, g);
-          tmem_ld_wait();
-          if (valid) {
-            const int cnt = min(16, half - c0);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float fv = f[i] + bias_s[c0 + i], gv = g[i] + bias_s[half + c0 + i];
-              const float a = is_elu ? (fv > 0.0f ? fv : ex2_approx(fv * 1.4426950408889634f) - 1.0f) : fmaxf(fv, 0.0f);
-              f[i] = a * fmaf(0.5f, tanh_approx(0.5f * gv), 0.5f);     // a * sigmoid(g)
-            }
-            store_row_bf16(o + c0, f, cnt, al8, al4);
-          }
-        }
-      }
+      tc_epilogue_tile(p.e, bias_s, cst_n, taddr, img, nt, valid, py, px, grp);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -435,6 +270,14 @@ void tc_choose_stage(TcWeights* w) {
   }
 }
 
+void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
+  e->y = c.y; e->out_dt = c.out_dt; e->out_c8 = c.out_c8;
+  e->Hout = c.Hout; e->Wout = c.Wout; e->ldo = c.ldo; e->choff = c.choff;
+  e->osy = c.osy; e->ooy = c.ooy; e->osx = c.osx; e->oox = c.oox;
+  e->epi = c.epi; e->scale = c.scale; e->colscale = c.colscale;
+  e->Cout = c.Cout; e->NT = NT;
+}
+
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes) {
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -461,10 +304,9 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   p.ksteps = tc_ksteps(w);
   p.w_img_bytes = w.img_bytes;
   p.w = reinterpret_cast<const uint8_t*>(w.data);
-  p.bias = c.bias; p.Cout = c.Cout;
-  p.y = c.y; p.out_dt = c.out_dt; p.Hout = c.Hout; p.Wout = c.Wout; p.ldo = c.ldo; p.choff = c.choff;
-  p.osy = c.osy; p.ooy = c.ooy; p.osx = c.osx; p.oox = c.oox;
-  p.epi = c.epi; p.scale = c.scale; p.colscale = c.colscale;
+  p.bias = c.bias;
+  fill_epi(c, w.NT, &p.e);
+  SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
   if (c.epi != EPI_LINEAR) {
     SE_REQUIRE(w.n_tiles == 1 && c.Cout % 2 == 0 && c.out_dt == DT_BF16, "gated epilogue needs one N tile, even Cout, bf16 out");
   }
@@ -473,7 +315,7 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   SE_REQUIRE(stages >= 2, "pipeline needs >= 2 stages");
   p.num_stages = stages;
-  *smem_bytes = 1024 + stages * stage_bytes + (2 * MAX_STAGES + 4) * 8 + 16 + (p.n_tiles * p.NT + 32) * 4 + 64;
+  *smem_bytes = 1024 + stages * stage_bytes + (2 * MAX_STAGES + 4) * 8 + 16 + 3 * (p.n_tiles * p.NT + 32) * 4 + 64;
   *out = p;
   return 0;
 }

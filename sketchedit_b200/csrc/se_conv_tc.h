@@ -51,19 +51,13 @@ struct TcParams {
   const uint8_t* w;
   int num_stages;
   const float* bias;
-  int Cout;
-  void* y;
-  int out_dt;
-  int Hout, Wout, ldo, choff;
-  int osy, ooy, osx, oox;
-  int epi;
-  float scale;
-  const float* colscale;
+  EpiParams e;
   unsigned long long* dbg;   // optional per-CTA role timers (SE_TC_DEBUG=1)
 };
 
 // pick (r64, r32) for a layer: as many units per stage as fit ~48 KB (SE_TC_STAGE_KB)
 void tc_choose_stage(TcWeights* w);
+void fill_epi(const ConvParams& c, int NT, EpiParams* e);
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes);
 int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream);
 

@@ -3,6 +3,8 @@
 //   MDGenerator.forward            reference models/networks/editline2_g.py:59-94
 //   DeepFillC2Generator.forward    reference models/networks/editline_g.py:119-221
 //   EditLine2Model inference       reference models/editline2_model.py:128-133,338-370
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <string>
@@ -11,6 +13,7 @@
 #include "../../include/sketchedit_b200.h"
 #include "se_common.cuh"
 #include "se_conv_direct.h"
+#include "se_conv_c8.h"
 #include "se_conv_tc.h"
 #include "se_misc.h"
 
@@ -117,8 +120,10 @@ struct ClassW {
   int8_t dy[MAX_TAPS], dx[MAX_TAPS];
   float* w_direct = nullptr;   // device fp32 [tap][Ci][CoutP]
   int CoutP = 0;
-  TcWeights tc;                // device bf16
+  TcWeights tc;                // device bf16 (se_conv_tc.cu: NHWC input; stride-2 layers and attention)
   bool has_tc = false;
+  C8Layer c8;                  // se_conv_c8.cu: channel-blocked input (every stride-1 layer on the bf16 path)
+  bool use_c8 = false;
   int osy = 1, ooy = 0, osx = 1, oox = 0;
 };
 
@@ -201,16 +206,26 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
   }
   cw.has_tc = (Ci % 8 == 0) && !L.is_head;
   if (cw.has_tc) {
-    TcWeights& tc = cw.tc;
-    tc.ntaps = cw.ntaps;
-    tc.n64 = Ci / 64;
-    int rem = Ci - 64 * tc.n64;
-    if (rem > 32) { ++tc.n64; rem = 0; }
-    tc.n32 = rem > 0 ? 1 : 0;
-    tc.NT = (Cout + 15) / 16 * 16;
-    tc.n_tiles = 1;
-    tc.img_bytes = 0;
-    tc_choose_stage(&tc);
+    cw.use_c8 = (s.stride == 1);
+    TcWeights* tcp;
+    if (cw.use_c8) {
+      int rc = c8_configure(&cw.c8, cw.ntaps, cw.dy, cw.dx, Ci, Cout, L.is_stem);
+      if (rc) return rc;
+      tcp = &cw.c8.w;
+    } else {
+      TcWeights& tc = cw.tc;
+      tc.ntaps = cw.ntaps;
+      tc.n64 = Ci / 64;
+      int rem = Ci - 64 * tc.n64;
+      if (rem > 32) { ++tc.n64; rem = 0; }
+      tc.n32 = rem > 0 ? 1 : 0;
+      tc.NT = (Cout + 15) / 16 * 16;
+      tc.n_tiles = 1;
+      tc.img_bytes = 0;
+      tc_choose_stage(&tc);
+      tcp = &tc;
+    }
+    TcWeights& tc = *tcp;
     // the exact (swizzled) shared-memory image of every pipeline stage, see se_conv_tc.h
     const int ksteps = tc_ksteps(tc), sb = tc_stage_b_bytes(tc);
     std::vector<uint16_t> img((size_t)ksteps * sb / 2, 0);
@@ -381,7 +396,12 @@ struct Ctx {
     }                                 \
   } while (0)
 
-struct View { void* p; int H, W, C, ld; };   // NHWC activation view (channels [0,C) at pitch ld)
+// activation view. c8 == 0: NHWC, channels [0,C) at pixel pitch ld. c8 == 1: [B][ld blocks][H][W][8], the view's
+// channels start at block cb_off.
+struct View { void* p; int H, W, C, ld; int c8 = 0; int cb_off = 0; };
+static inline View nhwc(void* p, int H, int W, int C, int ld) { View v; v.p = p; v.H = H; v.W = W; v.C = C; v.ld = ld; return v; }
+static inline View c8view(void* p, int H, int W, int C, int cbtot, int cb_off) { View v; v.p = p; v.H = H; v.W = W; v.C = C; v.ld = cbtot; v.c8 = 1; v.cb_off = cb_off; return v; }
+static inline size_t act_bytes(const struct Ctx& c, int H, int W, int C, int c8);
 
 static Layer* find_layer(se_model* m, char net, const std::string& name) {
   auto it = m->layers.find(std::string(1, net) + "." + name);
@@ -399,6 +419,7 @@ static Layer* find_ready(se_model* m, char net, const std::string& name) {
 
 static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw, double flops) {
   if (c.prec == SE_PREC_BF16_TC && cw.has_tc) {
+    auto go = [&]() -> int { return cw.use_c8 ? c8_launch(cp, cw.c8, c.stream) : tc_launch(cp, cw.tc, c.stream); };
     if (g_tc_timing) {
       if (g_ev_used == g_ev_pool.size()) {
         cudaEvent_t a, b;
@@ -408,13 +429,13 @@ static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw, double fl
       }
       auto& ev = g_ev_pool[g_ev_used++];
       SE_CUDA_OK(cudaEventRecord(ev.first, c.stream));
-      int rc = tc_launch(cp, cw.tc, c.stream);
+      int rc = go();
       if (rc) return rc;
       SE_CUDA_OK(cudaEventRecord(ev.second, c.stream));
       g_tc_flops += flops;
       return 0;
     }
-    return tc_launch(cp, cw.tc, c.stream);
+    return go();
   }
   ConvParams d = cp;
   d.w = cw.w_direct;
@@ -422,7 +443,20 @@ static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw, double fl
 }
 
 // one gated conv / deconv layer: in (Hi x Wi x Ci) -> out view (channels written at [choff, choff+cout_g))
-static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int choff) {
+// layout a layer wants for its input on the bf16 tensor-core path (stride-2 layers read NHWC, the rest C8)
+static int wants_c8(const Ctx& c, const Layer& L) { return (c.prec == SE_PREC_BF16_TC && !L.is_head && L.spec.stride == 1) ? 1 : 0; }
+static inline size_t act_bytes(const Ctx& c, int H, int W, int C, int c8) {
+  return c8 ? (size_t)c.B * ((C + 7) / 8) * H * W * 16 : (size_t)c.B * H * W * C * c.esz();
+}
+// the packed 8-channel network input (zero-padded rows of stem_wp(W) pixels): NHWC with C = ld = 8 for the CUDA-core
+// kernels, the same bytes seen as one channel block of width stem_wp(W) for the tensor-core path
+static View stem_view(const Ctx& c, void* p, int H, int W) {
+  if (c.prec == SE_PREC_BF16_TC) return c8view(p, H, W, 8, 1, 0);
+  return nhwc(p, H, W, 8, 8);
+}
+
+static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int choff, int out_c8 = 0) {
+  SE_REQUIRE(in.c8 == wants_c8(c, L), "activation layout mismatch at layer " + L.name);
   const Spec& s = L.spec;
   const int Ho = s.deconv ? in.H : (in.H + s.stride - 1) / s.stride;   // position grid
   const int Wo = s.deconv ? in.W : (in.W + s.stride - 1) / s.stride;
@@ -431,12 +465,17 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     memset(&cp, 0, sizeof(cp));
     cp.x = in.p; cp.in_dt = c.act_dt();
     cp.N = c.B; cp.Hi = in.H; cp.Wi = in.W; cp.Ci = L.Ci; cp.ldx = in.ld;
-    if (L.is_stem) {   // `in` is the packed 8-channel buffer with zero-padded rows of stem_wp(W) pixels
+    if (L.is_stem && !in.c8) {   // `in` is the packed 8-channel buffer with zero-padded rows of stem_wp(W) pixels
       cp.ldx = 8;
       cp.Wi = stem_wp(in.W) - 7;
       cp.x_row_pitch = (long long)stem_wp(in.W) * 8;
       cp.x_img_pitch = (long long)in.H * cp.x_row_pitch;
     }
+    if (in.c8) {
+      cp.in_c8 = 1; cp.x_cb_off = in.cb_off; cp.ldx = in.ld;
+      if (L.is_stem) cp.Wi = stem_wp(in.W);   // the window starts at buffer pixel x (image sits at x + STEM_PADL)
+    }
+    cp.out_c8 = out_c8;
     cp.Ho = Ho; cp.Wo = Wo; cp.stride = s.deconv ? 1 : s.stride;
     cp.ntaps = cw.ntaps;
     memcpy(cp.dy, cw.dy, sizeof(cp.dy));
@@ -451,6 +490,15 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     const double flops = 2.0 * c.B * Ho * Wo * (double)s.cout * s.cin * (s.deconv ? 9.0 / 4.0 : (double)s.k * s.k);
     CK(launch_conv(c, cp, cw, flops));
   }
+  static const bool dbg = getenv("SE_DEBUG_NAN") != nullptr;
+  if (dbg && !c.dry && c.act_dt() == DT_BF16) {
+    const int cg = s.cout / 2, Hout = Ho * L.cls[0].osy, Wout = Wo * L.cls[0].osx;
+    const long long n_out = out_c8 ? (long long)c.B * ldo * Hout * Wout * 8 : (long long)c.B * Hout * Wout * ldo;
+    const long long n_in = in.c8 ? (long long)c.B * in.ld * in.H * (L.is_stem ? stem_wp(in.W) : in.W) * 8 : (long long)c.B * in.H * in.W * in.ld;
+    fprintf(stderr, "[nan] %-28s in %dx%d c8=%d ld=%d nonfinite_in=%lld | out %dx%d c8=%d ld=%d choff=%d cg=%d nonfinite_out(buffer)=%lld use_c8=%d mode=%d res=%d\n", L.name.c_str(), in.H, in.W,
+            in.c8, in.ld, count_nonfinite_bf16(in.p, n_in, c.stream), Hout, Wout, out_c8, ldo, choff, cg, count_nonfinite_bf16(out, n_out, c.stream), (int)L.cls[0].use_c8,
+            L.cls[0].c8.mode, (int)L.cls[0].c8.resident);
+  }
   return 0;
 }
 
@@ -459,13 +507,15 @@ static void out_dims(const Spec& s, int H, int W, int* Ho, int* Wo) {
   else { *Ho = (H + s.stride - 1) / s.stride; *Wo = (W + s.stride - 1) / s.stride; }
 }
 
-// run a chain of gated layers; intermediate buffers come from the arena. The last layer writes to
-// (final_out, final_ld, final_choff) when given, else to a fresh buffer returned in *res.
+// run a chain of gated layers; intermediate buffers come from the arena. Each intermediate is written in the layout
+// its consumer wants. The last layer writes to (final_out, final_ld, final_choff, final_c8) when given, else to a
+// fresh buffer (layout final_c8) returned in *res.
 static int run_chain(Ctx& c, char net, const std::vector<std::string>& names, View in, bool free_in, Buf in_buf, View* res, Buf* res_buf,
-                     void* final_out = nullptr, int final_ld = 0, int final_choff = 0) {
+                     void* final_out = nullptr, int final_ld = 0, int final_choff = 0, int final_c8 = -1) {
   View cur = in;
   Buf cur_buf = in_buf;
   bool cur_owned = free_in;
+  if (final_c8 < 0) final_c8 = (c.prec == SE_PREC_BF16_TC) ? 1 : 0;
   for (size_t i = 0; i < names.size(); ++i) {
     Layer* L = find_ready(c.m, net, names[i]);
     SE_REQUIRE(L != nullptr, "unknown or unloaded layer " + names[i] + ": " + last_error());
@@ -476,13 +526,19 @@ static int run_chain(Ctx& c, char net, const std::vector<std::string>& names, Vi
     View nxt;
     Buf nb;
     if (last && final_out) {
-      nxt = View{final_out, Ho, Wo, cg, final_ld};
-      int rc = run_layer(c, *L, cur, final_out, final_ld, final_choff);
+      nxt = final_c8 ? c8view(final_out, Ho, Wo, cg, final_ld, final_choff / 8) : nhwc(final_out, Ho, Wo, cg, final_ld);
+      int rc = run_layer(c, *L, cur, final_out, final_ld, final_choff, final_c8);
       if (rc) return rc;
     } else {
-      nb = c.get((size_t)c.B * Ho * Wo * cg * c.esz());
-      nxt = View{nb.p, Ho, Wo, cg, cg};
-      int rc = run_layer(c, *L, cur, nb.p, cg, 0);
+      int oc8 = final_c8;
+      if (!last) {
+        Layer* nx = find_ready(c.m, net, names[i + 1]);
+        SE_REQUIRE(nx != nullptr, "unknown or unloaded layer " + names[i + 1]);
+        oc8 = wants_c8(c, *nx);
+      }
+      nb = c.get(act_bytes(c, Ho, Wo, cg, oc8));
+      nxt = oc8 ? c8view(nb.p, Ho, Wo, cg, (cg + 7) / 8, 0) : nhwc(nb.p, Ho, Wo, cg, cg);
+      int rc = run_layer(c, *L, cur, nb.p, oc8 ? (cg + 7) / 8 : cg, 0, oc8);
       if (rc) return rc;
     }
     if (cur_owned) c.put(cur_buf);
@@ -505,7 +561,7 @@ static int run_head(Ctx& c, char net, const std::string& name, const View& in, i
                     const float* mask_soft, float* out_nchw, float* out2, void* out_pack8) {
   Layer* L = find_ready(c.m, net, name);
   SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name + ": " + last_error());
-  CK(head(in.p, c.act_dt(), L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
+  CK(head(in.p, c.act_dt(), in.c8, L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
           out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, c.stream));
   return 0;
 }
@@ -514,7 +570,8 @@ static int run_head(Ctx& c, char net, const std::string& name, const View& in, i
 // cam_1 + cam_2 (reference splitcam.py:57-108,147-174) on an NHWC feature map f [B,h,w,C]:
 //   S = Q K^T  as a stride-2, 4x4-tap "convolution" of f with per-image kernels K   (utils.py:72-99)
 //   A = softmax_l(10 * S * m_l),  out = fold_sum(A V) as four sub-pixel 2x2 convolutions over A
-static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int out_ld, float* attn_out /*fp32 [B,L,N] or null*/) {
+static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int out_ld, float* attn_out /*fp32 [B,L,N] or null*/, int out_c8 = 0) {
+  SE_REQUIRE(f.c8 == 0, "attention reads an NHWC feature map");
   const int B = c.B, h = f.H, w = f.W, C = f.C;
   SE_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "attention map must be even-sized and >= 4");
   const int hs = (h - 4) / 2 + 1, ws = (w - 4) / 2 + 1, L = hs * ws;
@@ -524,7 +581,7 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
 
   Buf rnorm = c.get((size_t)B * C * 4);
   Buf colm = c.get((size_t)B * L * 4);
-  CK(plane_reduce(f.p, dt, B, h * w, C, f.ld, RED_RNORM, (float*)rnorm.p, c.stream));
+  CK(plane_reduce(f.p, dt, B, h * w, C, f.ld, 0, RED_RNORM, (float*)rnorm.p, c.stream));
   CK(cam_colmask(mask_s, (float*)colm.p, B, h, w, hs, ws, 0.1f, c.stream));
 
   // ---- keys
@@ -590,7 +647,8 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cp.Ho = h / 2; cp.Wo = w / 2; cp.stride = 1; cp.ntaps = 4;
     for (int t = 0; t < 4; ++t) { cp.dy[t] = (int8_t)(-(t / 2)); cp.dx[t] = (int8_t)(-(t % 2)); }
     cp.bias = nullptr; cp.Cout = C;
-    cp.y = out; cp.out_dt = dt; cp.Hout = h; cp.Wout = w; cp.ldo = out_ld; cp.choff = 0;
+    cp.y = out; cp.out_dt = dt; cp.Hout = h; cp.Wout = w; cp.ldo = out_c8 ? (C + 7) / 8 : out_ld; cp.choff = 0;
+    cp.out_c8 = out_c8;
     cp.osy = 2; cp.ooy = pc / 2; cp.osx = 2; cp.oox = pc % 2;
     cp.epi = EPI_LINEAR; cp.scale = 1.0f; cp.colscale = nullptr;
     ClassW cw;
@@ -620,7 +678,7 @@ static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, fl
   CK(pack8(x, guide, nullptr, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE, 1.0f, 0, c.stream));
   View x9;
   Buf b9;
-  int rc = run_chain(c, 'M', with_prefix("", kTrunk9), View{in8.p, H, W, 8, 8}, true, in8, &x9, &b9);
+  int rc = run_chain(c, 'M', with_prefix("", kTrunk9), stem_view(c, in8.p, H, W), true, in8, &x9, &b9);
   if (rc) return rc;
   if (x_stage1) {
     // image decoder consumes the conv9 output (editline2_g.py:76-77)
@@ -659,13 +717,16 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   const size_t e = c.esz();
 
   // ---- stage 1: coarse encoder + style ("warp-in") encoder -> 192-channel concat -> coarse decoder
+  const int tc = (c.prec == SE_PREC_BF16_TC) ? 1 : 0;
+  const int cat_ld = tc ? 24 : 192;                    // 192-channel concat buffers: 24 channel blocks or pixel pitch 192
+  auto cat_view = [&](void* p) { return tc ? c8view(p, h, w, 192, 24, 0) : nhwc(p, h, w, 192, 192); };
   Buf cat1 = c.get((size_t)c.B * h * w * 192 * e);
   {
     Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
     CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
     std::vector<std::string> names = with_prefix("", kTrunk9);
     names.push_back("conv10_atrous");
-    int rc = run_chain(c, 'G', names, View{in8.p, H, W, 8, 8}, true, in8, nullptr, nullptr, cat1.p, 192, 0);
+    int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, nullptr, nullptr, cat1.p, cat_ld, 0);
     if (rc) return rc;
   }
   {
@@ -676,11 +737,11 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     names.push_back("wconv10_atrous");
     View v;
     Buf b;
-    int rc = run_chain(c, 'G', names, View{in8.p, H, W, 8, 8}, true, in8, &v, &b);
+    int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, &v, &b);
     if (rc) return rc;
     Buf pooled = c.get((size_t)c.B * 96 * 4);
-    CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
-    CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, 192, 96, c.stream));
+    CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, v.c8, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
+    CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, cat_ld, 96, tc, c.stream));
     c.put(pooled);
     c.put(b);
   }
@@ -689,7 +750,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     View v16;
     Buf b16;
     int rc = run_chain(c, 'G', with_prefix("conv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}),
-                       View{cat1.p, h, w, 192, 192}, true, cat1, &v16, &b16);
+                       cat_view(cat1.p), true, cat1, &v16, &b16);
     if (rc) return rc;
     CK(fill_zero(xnow.p, xnow.bytes, c.stream));   // zero pad pixels of the packed stage-2 input
     rc = run_head(c, 'G', "conv17", v16, HEAD_COARSE, x, mask, nullptr, x_stage1, nullptr, xnow.p);
@@ -701,34 +762,34 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   {
     std::vector<std::string> names = with_prefix("x", kTrunk9);
     names.push_back("xconv10_atrous");
-    int rc = run_chain(c, 'G', names, View{xnow.p, H, W, 8, 8}, false, Buf(), nullptr, nullptr, cat2.p, 192, 0);
+    int rc = run_chain(c, 'G', names, stem_view(c, xnow.p, H, W), false, Buf(), nullptr, nullptr, cat2.p, cat_ld, 0);
     if (rc) return rc;
   }
   {
     View pm;
     Buf pmb;
     int rc = run_chain(c, 'G', with_prefix("pm", {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}),
-                       View{xnow.p, H, W, 8, 8}, true, xnow, &pm, &pmb);
+                       stem_view(c, xnow.p, H, W), true, xnow, &pm, &pmb, nullptr, 0, 0, opt[SE_OPT_USE_CAM] ? 0 : -1);
     if (rc) return rc;
     if (opt[SE_OPT_USE_CAM]) {
       Buf ms = c.get((size_t)c.B * h * w * 4);
       CK(avgpool4(mask, (float*)ms.p, c.B, H, W, c.stream));
       Buf camo = c.get((size_t)c.B * h * w * 96 * e);
-      rc = run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr);
+      rc = run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr, tc);
       if (rc) return rc;
       c.put(ms);
       c.put(pmb);
-      pm = View{camo.p, h, w, 96, 96};
+      pm = tc ? c8view(camo.p, h, w, 96, 12, 0) : nhwc(camo.p, h, w, 96, 96);
       pmb = camo;
     }
-    rc = run_chain(c, 'G', with_prefix("pm", {"conv9", "conv10"}), pm, true, pmb, nullptr, nullptr, cat2.p, 192, 96);
+    rc = run_chain(c, 'G', with_prefix("pm", {"conv9", "conv10"}), pm, true, pmb, nullptr, nullptr, cat2.p, cat_ld, 96);
     if (rc) return rc;
   }
   {
     View v16;
     Buf b16;
     int rc = run_chain(c, 'G', with_prefix("allconv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}),
-                       View{cat2.p, h, w, 192, 192}, true, cat2, &v16, &b16);
+                       cat_view(cat2.p), true, cat2, &v16, &b16);
     if (rc) return rc;
     if (composed) {
       rc = run_head(c, 'G', "allconv17", v16, HEAD_FINE, blend_img, nullptr, mask_soft, composed, x_stage2, nullptr);
@@ -903,10 +964,14 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
     const Spec& s = L->spec;
     const int dt = c.act_dt();
     const int Ci = L->is_head ? 12 : L->Ci;
-    Buf in = c.get(L->is_stem ? (size_t)B * H * stem_wp(W) * 8 * c.esz() : (size_t)B * H * W * Ci * c.esz());
+    const int in_c8 = wants_c8(c, *L);
+    Buf in = c.get(L->is_stem ? (size_t)B * H * stem_wp(W) * 8 * c.esz() : act_bytes(c, H, W, Ci, in_c8));
     if (L->is_stem) {
       CK(fill_zero(in.p, in.bytes, st));
       CK(nchw_to_stem8(x, in.p, dt, B, s.cin, H, W, stem_wp(W), STEM_PADL, st));
+    } else if (in_c8) {
+      if (s.cin % 8) CK(fill_zero(in.p, in.bytes, st));
+      CK(nchw_to_c8(x, in.p, B, s.cin, H * W, st));
     } else {
       CK(nchw_to_nhwc(x, in.p, dt, B, s.cin, H * W, Ci, 0, st));
     }
@@ -931,7 +996,8 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
     } else {
       const int cg = s.cout / 2;
       Buf o = c.get((size_t)B * Ho * Wo * cg * c.esz());
-      int r = run_layer(c, *L, View{in.p, H, W, L->is_stem ? 8 : Ci, L->is_stem ? 8 : Ci}, o.p, cg, 0);
+      View vin = L->is_stem ? stem_view(c, in.p, H, W) : (in_c8 ? c8view(in.p, H, W, Ci, (Ci + 7) / 8, 0) : nhwc(in.p, H, W, Ci, Ci));
+      int r = run_layer(c, *L, vin, o.p, cg, 0, 0);
       if (r) return r;
       CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, st));
       c.put(o);
@@ -954,7 +1020,7 @@ int se_contextual_attention_forward(const float* feat, const float* mask_s, int 
     Buf in = c.get((size_t)B * h * w * C * c.esz());
     CK(nchw_to_nhwc(feat, in.p, dt, B, C, h * w, C, 0, st));
     Buf o = c.get((size_t)B * h * w * C * c.esz());
-    int r = run_cam(c, View{in.p, h, w, C, C}, mask_s, o.p, C, attn);
+    int r = run_cam(c, nhwc(in.p, h, w, C, C), mask_s, o.p, C, attn);
     if (r) return r;
     CK(nhwc_to_nchw(o.p, dt, out, B, C, h * w, C, 0, st));
     c.put(o);

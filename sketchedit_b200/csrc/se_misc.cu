@@ -34,22 +34,30 @@ __global__ void pack8_kernel(const float* __restrict__ img, const float* __restr
   const long long by = j / Wp;
   const int x = xp - padl;
   if (x < 0 || x >= W) {
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(out + j * 8) = make_uint4(0, 0, 0, 0);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) out[j * 8 + c] = from_f<T>(0.0f);
+      for (int c = 0; c < 8; ++c) out[j * 8 + c] = from_f<T>(0.0f);
+    }
     return;
   }
   const long long b = by / H, pix = (by % H) * W + x;
   const long long i = b * HW + pix;
   const float m = mask ? mask[i] : 0.0f;
   const float a = img_mode == PACK_IMG_ONE ? 1.0f : (img_mode == PACK_IMG_ONE_MINUS_M ? 1.0f - m : m);
-  T v[8];
+  __align__(16) T v[8];
 #pragma unroll
   for (int c = 0; c < 3; ++c) v[c] = from_f<T>(img[(b * 3 + c) * HW + pix] * a);
   v[3] = from_f<T>(sketch ? sketch[i] * sketch_scale : 0.0f);
   v[4] = from_f<T>(write_mask ? m : 0.0f);
   v[5] = v[6] = v[7] = from_f<T>(0.0f);
+  if (sizeof(T) == 2) {
+    *reinterpret_cast<uint4*>(out + j * 8) = *reinterpret_cast<const uint4*>(v);   // 8 x bf16 = one 16 B store
+  } else {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) out[j * 8 + c] = v[c];
+    for (int c = 0; c < 8; ++c) out[j * 8 + c] = v[c];
+  }
 }
 
 int pack8(const float* img, const float* sketch, const float* mask, void* out, int dt, int B, int H, int W, int Wp, int padl,
@@ -71,7 +79,7 @@ template <typename T, int COUT>
 __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w /*[9][12][COUT]*/, const float* __restrict__ bias,
                             int B, int H, int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
                             const float* __restrict__ mask_soft, float* __restrict__ out_nchw, float* __restrict__ out2,
-                            T* __restrict__ out_pack8, int no_mask_coarse, int Wp, int padl) {
+                            T* __restrict__ out_pack8, int no_mask_coarse, int Wp, int padl, int in_c8) {
   __shared__ float ws[9 * 12 * COUT + COUT];
   for (int i = threadIdx.x; i < 9 * 12 * COUT; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < COUT) ws[9 * 12 * COUT + threadIdx.x] = bias[threadIdx.x];
@@ -88,10 +96,20 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
   for (int t = 0; t < 9; ++t) {
     const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
     if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    const T* xp = x + ((b * H + iy) * W + ix) * 12;
+    // NHWC: 12 contiguous channels; C8: two channel blocks [b][2][H][W][8] (channels 12..15 are padding)
+    const T* xp = in_c8 ? x + (((b * 2) * H + iy) * W + ix) * 8 : x + ((b * H + iy) * W + ix) * 12;
+    const long long blk = in_c8 ? (long long)H * W * 8 - 8 : 0;
+    __align__(16) T xl[16];
+    if (in_c8 && sizeof(T) == 2) {   // two 16 B loads instead of twelve 2 B loads
+      *reinterpret_cast<uint4*>(xl) = *reinterpret_cast<const uint4*>(xp);
+      *reinterpret_cast<uint4*>(xl + 8) = *reinterpret_cast<const uint4*>(xp + blk + 8);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) xl[c] = xp[c + (c >= 8 ? blk : 0)];
+    }
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
-      const float xv = to_f<T>(xp[c]);
+      const float xv = to_f<T>(xl[c]);
 #pragma unroll
       for (int o = 0; o < COUT; ++o) acc[o] = fmaf(xv, ws[(t * 12 + c) * COUT + o], acc[o]);
     }
@@ -129,16 +147,16 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
   }
 }
 
-int head(const void* x, int dt, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
+int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
          int Wp, int padl, cudaStream_t s) {
   const long long n = (long long)B * H * W;
   SE_REQUIRE(cout == 1 || cout == 3, "head cout");
   SE_DISPATCH_T(dt, {
     if (cout == 1)
-      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl);
+      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8);
     else
-      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl);
+      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8);
   });
   SE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -149,15 +167,17 @@ int head(const void* x, int dt, const float* w, const float* bias, int cout, int
 //   RED_MAX / RED_AVG      global pooling            (editline_g.py:160-165)
 //   RED_RNORM              1/sqrt(sum x^2 + 1e-8)    (splitcam.py:40)
 template <typename T>
-__global__ void plane_reduce_kernel(const T* __restrict__ x, int ldx, int C, int HW, int mode, float* __restrict__ out) {
+__global__ void plane_reduce_kernel(const T* __restrict__ x, int ldx, int c8, int C, int HW, int mode, float* __restrict__ out) {
   __shared__ float red[8][33];
   const int b = blockIdx.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = (mode == RED_MAX) ? -INFINITY : 0.0f;
   if (c < C) {
-    const T* xp = x + (size_t)b * HW * ldx + c;
+    // NHWC: pixel pitch ldx; C8: [b][ldx blocks][HW][8]
+    const T* xp = c8 ? x + ((size_t)b * ldx + (c >> 3)) * HW * 8 + (c & 7) : x + (size_t)b * HW * ldx + c;
+    const size_t pitch = c8 ? 8 : ldx;
     for (int p = threadIdx.y; p < HW; p += 8) {
-      const float v = to_f<T>(xp[(size_t)p * ldx]);
+      const float v = to_f<T>(xp[(size_t)p * pitch]);
       if (mode == RED_MAX) acc = fmaxf(acc, v);
       else if (mode == RED_AVG) acc += v;
       else acc = fmaf(v, v, acc);
@@ -176,9 +196,56 @@ __global__ void plane_reduce_kernel(const T* __restrict__ x, int ldx, int C, int
   }
 }
 
-int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int mode, float* out, cudaStream_t s) {
+// C8 bf16: one block per (image, channel block): the plane is HW contiguous 16 B pixels
+__global__ void plane_reduce_c8_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int C, int HW, int mode, float* __restrict__ out) {
+  __shared__ float red[8][8];
+  const int b = blockIdx.y, cb = blockIdx.x;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + ((size_t)b * ldx + cb) * HW * 8);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = (mode == RED_MAX) ? -INFINITY : 0.0f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const uint4 q = xp[p];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = __bfloat1622float2(h[i]);
+      if (mode == RED_MAX) { acc[2 * i] = fmaxf(acc[2 * i], v.x); acc[2 * i + 1] = fmaxf(acc[2 * i + 1], v.y); }
+      else if (mode == RED_AVG) { acc[2 * i] += v.x; acc[2 * i + 1] += v.y; }
+      else { acc[2 * i] = fmaf(v.x, v.x, acc[2 * i]); acc[2 * i + 1] = fmaf(v.y, v.y, acc[2 * i + 1]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    for (int o = 16; o; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, acc[i], o);
+      acc[i] = (mode == RED_MAX) ? fmaxf(acc[i], t) : acc[i] + t;
+    }
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+    for (int i = 0; i < 8; ++i) red[wid][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float r = red[0][threadIdx.x];
+    for (int j = 1; j < nw; ++j) r = (mode == RED_MAX) ? fmaxf(r, red[j][threadIdx.x]) : r + red[j][threadIdx.x];
+    if (mode == RED_AVG) r /= (float)HW;
+    if (mode == RED_RNORM) r = 1.0f / sqrtf(r + 1e-8f);
+    const int c = cb * 8 + threadIdx.x;
+    if (c < C) out[(size_t)b * C + c] = r;
+  }
+}
+
+// NHWC bf16 with C % 8 == 0: blocks over (pixel slices, image); partial results combined with float atomics
+// (max: order-free; sums: used for the L2 norm only where the bf16 path tolerates re-association)
+int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int c8, int mode, float* out, cudaStream_t s) {
+  if (c8 && dt == DT_BF16) {
+    dim3 grid((C + 7) / 8, B);
+    plane_reduce_c8_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, C, HW, mode, out);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(cdiv(C, 32), B), block(32, 8);
-  SE_DISPATCH_T(dt, (plane_reduce_kernel<T><<<grid, block, 0, s>>>((const T*)x, ldx, C, HW, mode, out)));
+  SE_DISPATCH_T(dt, (plane_reduce_kernel<T><<<grid, block, 0, s>>>((const T*)x, ldx, c8, C, HW, mode, out)));
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -186,18 +253,28 @@ int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int mode,
 // nearest 1x1 -> h x w broadcast of the pooled vector into channels [choff, choff+C) of an NHWC map
 // (editline_g.py:166-167: interpolate + cat).
 template <typename T>
-__global__ void broadcast_kernel(const float* __restrict__ v, T* __restrict__ y, int C, int HW, int ldo, int choff, long long total) {
+__global__ void broadcast_kernel(const float* __restrict__ v, T* __restrict__ y, int C, int HW, int ldo, int choff, int c8, long long total) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
+  if (c8) {   // [b][ldo blocks][HW][8]: i enumerates (b, c/8, p, c%8) so that consecutive threads write consecutive bytes
+    const int c7 = (int)(i & 7);
+    long long r = i >> 3;
+    const long long p = r % HW; r /= HW;
+    const int cb = (int)(r % (C >> 3));
+    const long long b = r / (C >> 3);
+    y[((b * ldo + (choff >> 3) + cb) * HW + p) * 8 + c7] = from_f<T>(v[b * C + cb * 8 + c7]);
+    return;
+  }
   const int c = (int)(i % C);
   const long long pix = i / C;
   const long long b = pix / HW;
   y[pix * ldo + choff + c] = from_f<T>(v[b * C + c]);
 }
 
-int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, cudaStream_t s) {
+int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, int c8, cudaStream_t s) {
   const long long total = (long long)B * HW * C;
-  SE_DISPATCH_T(dt, (broadcast_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(v, (T*)y, C, HW, ldo, choff, total)));
+  SE_REQUIRE(!c8 || (C % 8 == 0 && choff % 8 == 0), "C8 broadcast needs whole channel blocks");
+  SE_DISPATCH_T(dt, (broadcast_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(v, (T*)y, C, HW, ldo, choff, c8, total)));
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -248,31 +325,37 @@ int cam_colmask(const float* mask_s, float* out, int B, int h, int w, int hs, in
 template <typename T>
 __global__ void cam_pack_k_tc_kernel(const T* __restrict__ f, const float* __restrict__ rnorm, uint8_t* __restrict__ out,
                                      int B, int h, int w, int C, int ws, int L, int Lpad, int r64, int r32, long long total) {
+  // one thread = 8 consecutive channels (one 16 B swizzle chunk) of one key pixel and tap
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c = (int)(i % C);
-  long long r = i / C;
+  const int C8n = C >> 3;
+  const int co = (int)(i % C8n);
+  long long r = i / C8n;
   const int l = (int)(r % Lpad); r /= Lpad;
   const int tap = (int)(r % 16);
   const long long b = r / 16;
-  float v = 0.0f;
+  const int c = co * 8;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = 0.0f;
   if (l < L) {
     const int ly = l / ws, lx = l % ws, u = tap / 4, vv = tap % 4;
-    v = to_f<T>(f[((b * h + 2 * ly + u) * w + 2 * lx + vv) * C + c]) * rnorm[b * C + c];
+    const T* src = f + ((b * h + 2 * ly + u) * w + 2 * lx + vv) * C + c;
+    const float* rn = rnorm + b * C + c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = to_f<T>(src[k]) * rn[k];
   }
-  const int NT = 128, n64 = C / 64, n32 = (C % 64) ? 1 : 0;
+  const int NT = 128, n64 = C / 64;
   const int ksteps = n64 ? 16 * n64 / r64 : 16 / r32;
   const int sb = NT * (r64 * 128 + r32 * 64);
   const int nt = l / NT, n = l % NT;
-  int ks, j;
-  bool is64 = c < n64 * 64;
-  int k;
-  if (is64) { const int u = tap * n64 + c / 64; ks = u / r64; j = u % r64; k = c % 64; }
-  else { ks = tap / r32; j = tap % r32; k = c - n64 * 64; }
+  int ks, j, k0;
+  const bool is64 = c < n64 * 64;
+  if (is64) { const int uu = tap * n64 + c / 64; ks = uu / r64; j = uu % r64; k0 = c % 64; }
+  else { ks = tap / r32; j = tap % r32; k0 = c - n64 * 64; }
   const size_t img_bytes = (size_t)(Lpad / NT) * ksteps * sb;
-  uint8_t* dst = out + (size_t)b * img_bytes + ((size_t)nt * ksteps + ks) * sb + tc_b_image_offset(NT, n64 ? r64 : 0, is64, j, n, k);
-  *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(v);
-  (void)n32;
+  uint8_t* dst = out + (size_t)b * img_bytes + ((size_t)nt * ksteps + ks) * sb + tc_b_image_offset(NT, n64 ? r64 : 0, is64, j, n, k0);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
 // direct layout: fp32 [b][tap][c][CoutP]
@@ -299,7 +382,8 @@ int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layo
   const long long total = (long long)B * 16 * C * Lpad;
   if (tc_layout) {
     SE_REQUIRE(C % 32 == 0 && Lpad % 128 == 0, "C % 32, Lpad % 128");
-    SE_DISPATCH_T(dt, (cam_pack_k_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, r32, total)));
+    const long long chunks = total / 8;
+    SE_DISPATCH_T(dt, (cam_pack_k_tc_kernel<T><<<cdiv(chunks, 256), 256, 0, s>>>((const T*)f, rnorm, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, r32, chunks)));
   } else {
     SE_DISPATCH_T(dt, (cam_pack_k_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (float*)out, B, h, w, C, ws, L, Lpad, total)));
   }
@@ -315,24 +399,33 @@ int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layo
 template <typename T>
 __global__ void cam_pack_v_tc_kernel(const T* __restrict__ f, uint8_t* __restrict__ out, int B, int h, int w, int C, int ws,
                                      int L, int Lpad, int r64, long long pc_bytes, long long total) {
+  // one thread = 8 consecutive keys (one 16 B swizzle chunk) of one channel row; the 8 chunks of a 128 B row are
+  // written by 8 adjacent threads
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c = (int)(i % C);
-  long long r = i / C;
-  const int l = (int)(r % Lpad); r /= Lpad;
+  const int lo = (int)(i % (Lpad >> 3));
+  long long r = i / (Lpad >> 3);
+  const int c = (int)(r % C); r /= C;
   const int tap = (int)(r % 4); r /= 4;
   const long long b = r % B;
   const int pc = (int)(r / B);
-  float v = 0.0f;
-  if (l < L) {
-    const int ly = l / ws, lx = l % ws, py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
-    v = to_f<T>(f[((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + c]);
+  const int py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int l = lo * 8 + k;
+    v[k] = 0.0f;
+    if (l < L) {
+      const int ly = l / ws, lx = l % ws;
+      v[k] = to_f<T>(f[((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + c]);
+    }
   }
   const int NT = (C + 15) / 16 * 16, n64 = Lpad / 64;
   const int ksteps = 4 * n64 / r64, sb = NT * r64 * 128;
-  const int u = tap * n64 + l / 64, ks = u / r64, j = u % r64;
-  uint8_t* dst = out + (size_t)pc * pc_bytes + (size_t)b * ((size_t)ksteps * sb) + (size_t)ks * sb + tc_b_image_offset(NT, r64, true, j, c, l % 64);
-  *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(v);
+  const int l0 = lo * 8;
+  const int u = tap * n64 + l0 / 64, ks = u / r64, j = u % r64;
+  uint8_t* dst = out + (size_t)pc * pc_bytes + (size_t)b * ((size_t)ksteps * sb) + (size_t)ks * sb + tc_b_image_offset(NT, r64, true, j, c, l0 % 64);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
 // direct layout: fp32 [pc][b][tap][l (Ci = Lpad)][CoutP = C]
@@ -361,7 +454,8 @@ int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, in
   if (tc_layout) {
     SE_REQUIRE(Lpad % 64 == 0, "Lpad % 64");
     if (C % 16) SE_CUDA_OK(cudaMemsetAsync(out, 0, 4 * pc_bytes, s));   // padded N rows
-    SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes, total)));
+    const long long chunks = total / 8;
+    SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(chunks, 256), 256, 0, s>>>((const T*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes, chunks)));
   } else {
     SE_DISPATCH_T(dt, (cam_pack_v_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (float*)out, B, h, w, C, ws, L, Lpad, total)));
   }
@@ -373,27 +467,55 @@ int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, in
 // zero padding (splitcam.py:105; the scale 10 and the key mask are already applied by the GEMM epilogue).
 template <typename T>
 __global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, T* __restrict__ P, int ldp, int L) {
+  // one 256-thread block per row; up to SM_MAXV values per thread stay in registers (rows <= 256*SM_MAXV keys),
+  // longer rows fall back to re-reading
+  constexpr int SM_MAXV = 16;
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* s = S + row * lds;
   T* p = P + row * ldp;
+  const bool fits = L <= 256 * SM_MAXV;
+  float v[SM_MAXV];
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, s[i]);
+#pragma unroll
+  for (int k = 0; k < SM_MAXV; ++k) {
+    const int i = threadIdx.x + k * 256;
+    v[k] = (fits && i < L) ? s[i] : -INFINITY;
+    mx = fmaxf(mx, v[k]);
+  }
+  if (!fits)
+    for (int i = threadIdx.x; i < L; i += 256) mx = fmaxf(mx, s[i]);
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
   mx = red[0];
-  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
   __syncthreads();
   float sum = 0.0f;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) sum += expf(s[i] - mx);
+  if (fits) {
+#pragma unroll
+    for (int k = 0; k < SM_MAXV; ++k) {
+      v[k] = expf(v[k] - mx);      // exp(-inf) = 0 for the padding lanes
+      sum += v[k];
+    }
+  } else {
+    for (int i = threadIdx.x; i < L; i += 256) sum += expf(s[i] - mx);
+  }
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
   __syncthreads();
   sum = 0.0f;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sum += red[i];
+  for (int i = 0; i < 8; ++i) sum += red[i];
   const float inv = 1.0f / sum;
-  for (int i = threadIdx.x; i < ldp; i += blockDim.x) p[i] = from_f<T>(i < L ? expf(s[i] - mx) * inv : 0.0f);
+  if (fits) {
+#pragma unroll
+    for (int k = 0; k < SM_MAXV; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < ldp) p[i] = from_f<T>(i < L ? v[k] * inv : 0.0f);
+    }
+  } else {
+    for (int i = threadIdx.x; i < ldp; i += 256) p[i] = from_f<T>(i < L ? expf(s[i] - mx) * inv : 0.0f);
+  }
 }
 
 int softmax_rows(const float* S, int lds, void* P, int dt, int ldp, long long rows, int L, cudaStream_t s) {
@@ -443,6 +565,24 @@ int nchw_to_stem8(const float* x, void* y, int dt, int B, int cin, int H, int W,
   return 0;
 }
 
+// NCHW fp32 -> C8 bf16 [B][ceil(C/8)][HW][8] (padding channels untouched: zero the buffer first when C % 8)
+__global__ void nchw_to_c8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int HW, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i % HW;
+  long long r = i / HW;
+  const int c = (int)(r % C);
+  const long long b = r / C;
+  const int CB = (C + 7) / 8;
+  y[((b * CB + (c >> 3)) * HW + p) * 8 + (c & 7)] = __float2bfloat16(x[i]);
+}
+int nchw_to_c8(const float* x, void* y, int B, int C, int HW, cudaStream_t s) {
+  const long long total = (long long)B * C * HW;
+  nchw_to_c8_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, (__nv_bfloat16*)y, C, HW, total);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s) {
   const long long total = (long long)B * C * HW;
   SE_DISPATCH_T(dt, (nchw_to_nhwc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, (T*)y, C, HW, ldo, choff, total)));
@@ -475,6 +615,27 @@ int to_uint8(const float* comp, const float* mask, unsigned char* bgr, unsigned 
   to_uint8_kernel<<<cdiv(B * HW, 256), 256, 0, s>>>(comp, mask, bgr, mk, B, HW);
   SE_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// debug: number of non-finite bf16 values in a buffer
+__global__ void count_nonfinite_kernel(const __nv_bfloat16* __restrict__ x, long long n, unsigned long long* out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  unsigned long long c = 0;
+  for (; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __bfloat162float(x[i]);
+    if (!(fabsf(v) <= 3.0e38f)) ++c;
+  }
+  if (c) atomicAdd(out, c);
+}
+long long count_nonfinite_bf16(const void* x, long long n, cudaStream_t s) {
+  static unsigned long long* d = nullptr;
+  if (!d) cudaMalloc(&d, 8);
+  cudaMemsetAsync(d, 0, 8, s);
+  count_nonfinite_kernel<<<256, 256, 0, s>>>((const __nv_bfloat16*)x, n, d);
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  return (long long)h;
 }
 
 // zero-fill helper for padded channel tails

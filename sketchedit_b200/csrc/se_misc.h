@@ -10,11 +10,11 @@ enum { RED_MAX = 0, RED_AVG = 1, RED_RNORM = 2 };
 
 int pack8(const float* img, const float* sketch, const float* mask, void* out, int dt, int B, int H, int W, int Wp, int padl,
           int img_mode, float sketch_scale, int write_mask, cudaStream_t s);
-int head(const void* x, int dt, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
+int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
          int Wp, int padl, cudaStream_t s);
-int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int mode, float* out, cudaStream_t s);
-int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, cudaStream_t s);
+int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int c8, int mode, float* out, cudaStream_t s);
+int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, int c8, cudaStream_t s);
 int avgpool4(const float* m, float* out, int B, int H, int W, cudaStream_t s);
 int cam_colmask(const float* mask_s, float* out, int B, int h, int w, int hs, int ws, float th, cudaStream_t s);
 int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L,
@@ -23,9 +23,11 @@ int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, in
                long long pc_bytes, cudaStream_t s);
 int softmax_rows(const float* S, int lds, void* P, int dt, int ldp, long long rows, int L, cudaStream_t s);
 int nchw_to_stem8(const float* x, void* y, int dt, int B, int cin, int H, int W, int Wp, int padl, cudaStream_t s);
+int nchw_to_c8(const float* x, void* y, int B, int C, int HW, cudaStream_t s);
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s);
 int nhwc_to_nchw(const void* x, int dt, float* y, int B, int C, int HW, int ldx, int choff, cudaStream_t s);
 int to_uint8(const float* comp, const float* mask, unsigned char* bgr, unsigned char* mk, int B, int H, int W, cudaStream_t s);
+long long count_nonfinite_bf16(const void* x, long long n, cudaStream_t s);
 int fill_zero(void* p, size_t bytes, cudaStream_t s);
 
 }  // namespace se

@@ -1,0 +1,282 @@
+// Device-side building blocks shared by the tcgen05 convolution kernels (se_conv_tc.cu: NHWC input,
+// se_conv_c8.cu: channel-blocked input): mbarrier / TMA / tcgen05 PTX wrappers and the fused epilogue.
+#pragma once
+#include "se_common.cuh"
+
+namespace se {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("se_conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// linear global -> shared bulk copy (bytes % 16 == 0), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// one lane of a fully converged warp (the warp stays converged: the compiler keeps addresses / descriptors
+// in uniform registers instead of broadcasting them lane by lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// predicated forms: the warp stays converged (no divergent branch around the issue sequence), so descriptor
+// arithmetic stays on the uniform datapath; only the elected lane (lead != 0) actually issues
+__device__ __forceinline__ void umma_bf16_if(uint32_t lead, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+// same, descriptors passed as 32-bit halves (keeps the address arithmetic 32-bit / uniform)
+__device__ __forceinline__ void umma_bf16_if32(uint32_t lead, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t lead, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(lead)
+      : "memory");
+}
+
+// mbarrier arrives once all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// must be executed before the registers written by tmem_ld16 are read
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// write cnt (<= 16) consecutive channels of one pixel; static register indexing only (no local memory)
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* o, const float (&r)[16], int cnt, bool al8, bool al4) {
+  if (cnt == 16 && al8) {
+    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+    *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]), pack_bf16x2(r[14], r[15]));
+  } else if (al4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * j + 4 <= cnt) *reinterpret_cast<uint2*>(o + 4 * j) = make_uint2(pack_bf16x2(r[4 * j], r[4 * j + 1]), pack_bf16x2(r[4 * j + 2], r[4 * j + 3]));
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i >= (cnt & ~3) && i < cnt) o[i] = __float2bfloat16(r[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cnt) o[i] = __float2bfloat16(r[i]);
+  }
+}
+__device__ __forceinline__ void store_row_f32(float* o, const float (&r)[16], int cnt, bool al4) {
+  if (cnt == 16 && al4) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cnt) o[i] = r[i];
+  }
+}
+
+
+constexpr int TC_NUM_THREADS = 128 + 128 * 2;   // 4 role warps + 2 epilogue groups of 4 warps (== TC_THREADS below)
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_ACC_STRIDE = 256;   // TMEM columns between the two accumulator stages
+constexpr int TC_MAX_STAGES = 8;
+
+// ------------------------------------------------------------------------------------------ epilogue
+// write up to 16 consecutive channels [c, c+cnt) of one output pixel; v[i >= cnt] must be 0 for C8 (pads are stored)
+__device__ __forceinline__ void epi_store16(const EpiParams& e, int img, int oy, int ox, int c, const float (&v)[16], int cnt) {
+  if (e.out_c8) {
+    // two channel blocks of 8: 16 B each, one plane (Hout*Wout*8 elements) apart
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(e.y);
+    const size_t plane = (size_t)e.Hout * e.Wout * 8;
+    const size_t o = (((size_t)img * e.ldo + ((e.choff + c) >> 3)) * e.Hout + oy) * e.Wout * 8 + (size_t)ox * 8;
+    *reinterpret_cast<uint4*>(base + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    if (cnt > 8)
+      *reinterpret_cast<uint4*>(base + o + plane) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    return;
+  }
+  const size_t opix = ((size_t)img * e.Hout + oy) * e.Wout + ox;
+  const bool al4 = ((e.ldo | e.choff) & 3) == 0, al8 = ((e.ldo | e.choff) & 7) == 0;
+  if (e.out_dt == DT_F32) store_row_f32(reinterpret_cast<float*>(e.y) + opix * e.ldo + e.choff + c, v, cnt, al4);
+  else store_row_bf16(reinterpret_cast<__nv_bfloat16*>(e.y) + opix * e.ldo + e.choff + c, v, cnt, al8, al4);
+}
+
+constexpr int TC_EPI_GROUPS = 2;                                  // epilogue warps = 4 * groups (each group: 4 warps = 128 lanes)
+constexpr int TC_EPI_THREADS = 128 * TC_EPI_GROUPS;
+constexpr int TC_THREADS = 128 + TC_EPI_THREADS;                   // warps 0-3: producer / MMA / TMEM alloc / spare
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// Epilogue constants in shared memory, three float arrays of `n` entries each:
+//   [0,n)  bias b    [n,2n)  b * log2(e) (ELU exponent)    [2n,3n)  0.5 * b (sigmoid-as-tanh argument)
+__device__ __forceinline__ void epi_fill_constants(float* cst, int n, const float* bias, int Cout, int tid, int nthreads) {
+  for (int i = tid; i < n; i += nthreads) {
+    const float b = (bias != nullptr && i < Cout) ? bias[i] : 0.0f;
+    cst[i] = b;
+    cst[n + i] = b * 1.4426950408889634f;
+    cst[2 * n + i] = 0.5f * b;
+  }
+}
+
+// Drain one accumulator tile (this thread = TMEM lane = one output position) and apply the fused epilogue.
+//   gated : out[c] = act(acc[c] + b[c]) * sigmoid(acc[c + Cout/2] + b[c + Cout/2])   (reference utils.py:29-32)
+//           sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 (one MUFU), ELU's exp as ex2 with the bias folded into the FMA
+//   linear: out[c] = (acc[c] + b[c]) * scale * colscale[img][c]
+// The 16-column chunks of a tile are dealt round-robin to `nsplit` warp groups (this one is `grp`); nsplit == 1 means
+// this group drains the whole tile (the groups then alternate tiles).
+__device__ __forceinline__ void tc_epilogue_tile(const EpiParams& e, const float* cst, int cst_n, uint32_t taddr, int img, int nt, bool valid,
+                                                 int py, int px, int grp, int nsplit = TC_EPI_GROUPS) {
+  const int oy = py * e.osy + e.ooy, ox = px * e.osx + e.oox;
+  if (e.epi == EPI_LINEAR) {
+    const int n0 = nt * e.NT;
+    const float* cs = e.colscale ? e.colscale + (size_t)img * e.Cout : nullptr;
+    for (int c0 = grp * 16; c0 < e.NT; c0 += 16 * nsplit) {
+      const int cb = n0 + c0;
+      if (cb >= e.Cout) break;
+      float v[16];
+      tmem_ld16(taddr + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+        const int cnt = min(16, e.Cout - cb);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float sc = e.scale;
+          if (cs != nullptr && i < cnt) sc *= __ldg(cs + cb + i);
+          v[i] = (i < cnt) ? (v[i] + cst[cb + i]) * sc : 0.0f;
+        }
+        epi_store16(e, img, oy, ox, cb, v, cnt);
+      }
+    }
+  } else {
+    const int half = e.Cout >> 1;
+    const bool is_elu = (e.epi == EPI_GATE_ELU);
+    const uint32_t cs0 = smem_u32(cst);
+    for (int c0 = grp * 16; c0 < half; c0 += 16 * nsplit) {
+      float f[16], g[16];
+      tmem_ld16(taddr + c0, f);
+      tmem_ld16(taddr + half + c0, g);
+      tmem_ld_wait();
+      if (valid) {
+        const int cnt = min(16, half - c0);
+        const bool al = ((half & 3) == 0);   // 16 B aligned constant rows (c0 is a multiple of 16)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float b4[4], bl4[4], hb4[4];
+          if (al) {
+            const float4 b = lds128(cs0 + (c0 + 4 * q) * 4), bl = lds128(cs0 + (cst_n + c0 + 4 * q) * 4);
+            const float4 hb = lds128(cs0 + (2 * cst_n + half + c0 + 4 * q) * 4);
+            b4[0] = b.x; b4[1] = b.y; b4[2] = b.z; b4[3] = b.w;
+            bl4[0] = bl.x; bl4[1] = bl.y; bl4[2] = bl.z; bl4[3] = bl.w;
+            hb4[0] = hb.x; hb4[1] = hb.y; hb4[2] = hb.z; hb4[3] = hb.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              b4[i] = cst[c0 + 4 * q + i];
+              bl4[i] = cst[cst_n + c0 + 4 * q + i];
+              hb4[i] = cst[2 * cst_n + half + c0 + 4 * q + i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = 4 * q + i;
+            const float fv = f[k] + b4[i];
+            const float ex = ex2_approx(fmaf(f[k], 1.4426950408889634f, bl4[i])) - 1.0f;
+            const float a = is_elu ? (fv > 0.0f ? fv : ex) : fmaxf(fv, 0.0f);
+            const float sg = fmaf(0.5f, tanh_approx(fmaf(g[k], 0.5f, hb4[i])), 0.5f);     // sigmoid(g + b)
+            f[k] = (k < cnt) ? a * sg : 0.0f;
+          }
+        }
+        epi_store16(e, img, oy, ox, c0, f, cnt);
+      }
+    }
+  }
+}
+
+}  // namespace se
