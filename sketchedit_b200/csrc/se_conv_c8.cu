@@ -127,12 +127,16 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
     int stage = 0, iter = 0;
     uint32_t phase = 0;
     long long t_wait = 0, t_begin = clock64();
+    // tile coordinates advance incrementally by gridDim.x tiles (mixed radix step), no per-tile integer division
+    int tx = blockIdx.x % p.tiles_x, ty = (blockIdx.x / p.tiles_x) % p.tiles_y, img = blockIdx.x / (p.tiles_x * p.tiles_y);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      int rest = tile;
-      const int tx = rest % p.tiles_x;
-      rest /= p.tiles_x;
-      const int ty = rest % p.tiles_y;
-      const int img = rest / p.tiles_y;
+      if (tile != (int)blockIdx.x) {
+        tx += p.step_x;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+        ty += p.step_y;
+        if (ty >= p.tiles_y) { ty -= p.tiles_y; ++img; }
+        img += p.step_img;
+      }
       const int x0 = tx * C8_TW, y0 = ty * C8_TH;
       if (halo) {
         const int ab = (p.a_bufs == 2) ? (iter & 1) : 0;               // no integer division: keeps the value uniform
@@ -252,16 +256,20 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
     // ==================================================================== epilogue
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
+    const bool fast_epi = epi_fast_ok(p.e);
     const int row = q * 32 + lane;
     const int ry = row / C8_TW, rx = row % C8_TW;
     int iter = 0;
     long long t_wacc = 0, t_begin = clock64();
+    int tx = blockIdx.x % p.tiles_x, ty = (blockIdx.x / p.tiles_x) % p.tiles_y, img = blockIdx.x / (p.tiles_x * p.tiles_y);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      int rest = tile;
-      const int tx = rest % p.tiles_x;
-      rest /= p.tiles_x;
-      const int ty = rest % p.tiles_y;
-      const int img = rest / p.tiles_y;
+      if (tile != (int)blockIdx.x) {
+        tx += p.step_x;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+        ty += p.step_y;
+        if (ty >= p.tiles_y) { ty -= p.tiles_y; ++img; }
+        img += p.step_img;
+      }
       if (epi_split == 1 && (iter & 1) != grp) continue;      // tile-alternating groups
       const int as = iter & (acc_stages - 1);
       const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
@@ -272,7 +280,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_stride;
       const int py = ty * C8_TH + ry, px = tx * C8_TW + rx;
       const bool valid = (py < p.Ho) && (px < p.Wo);
-      tc_epilogue_tile(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
+      if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
+      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -465,6 +474,9 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   }
   const int total_tiles = p.N * p.tiles_x * p.tiles_y;
   const int grid = total_tiles < g_sms ? total_tiles : g_sms;
+  p.step_x = grid % p.tiles_x;
+  p.step_y = (grid / p.tiles_x) % p.tiles_y;
+  p.step_img = grid / (p.tiles_x * p.tiles_y);
   static const bool dbg_on = getenv("SE_TC_DEBUG") != nullptr;
   static unsigned long long* dbg_buf = nullptr;
   if (dbg_on) {

@@ -23,6 +23,7 @@ struct C8Layer {
 struct C8Params {
   int N, Ho, Wo;
   int tiles_x, tiles_y;
+  int step_x, step_y, step_img;   // gridDim.x decomposed in (tiles_x, tiles_y, images): incremental tile decode
   int ntaps;
   int8_t dy[MAX_TAPS], dx[MAX_TAPS];
   int n64, n32, r64, r32, NT, ksteps;

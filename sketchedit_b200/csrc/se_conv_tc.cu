@@ -187,6 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
     // ==================================================================== epilogue
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int grp = (warp - 4) >> 2;            // which share of the 16-column chunks this warp drains
+    const bool fast_epi = epi_fast_ok(p.e);
     const int row = q * 32 + lane;             // tile row == TMEM lane == output position in tile
     const int ry = row / TILE_W, rx = row % TILE_W;
     int iter = 0;
@@ -207,7 +208,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
       const int py = ty * TILE_H + ry, px = tx * TILE_W + rx;
       const bool valid = (py < p.Ho) && (px < p.Wo);
-      tc_epilogue_tile(p.e, bias_s, cst_n, taddr, img, nt, valid, py, px, grp);
+      if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, nt, valid, py, px, grp);
+      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, nt, valid, py, px, grp);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }

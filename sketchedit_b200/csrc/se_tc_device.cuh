@@ -166,7 +166,10 @@ constexpr int TC_ACC_STRIDE = 256;   // TMEM columns between the two accumulator
 constexpr int TC_MAX_STAGES = 8;
 
 // ------------------------------------------------------------------------------------------ epilogue
-// write up to 16 consecutive channels [c, c+cnt) of one output pixel; v[i >= cnt] must be 0 for C8 (pads are stored)
+// write up to 16 consecutive channels [c, c+cnt) of one output pixel; v[i >= cnt] must be 0 for C8 (pads are stored).
+// kFast: the launch guarantees bf16 output and (C8, or NHWC with 16 B aligned rows and cnt in {8, 16}): the store is
+// one or two 16 B vectors and nothing else (the epilogue runs one warp per scheduler: every instruction counts).
+template <bool kFast>
 __device__ __forceinline__ void epi_store16(const EpiParams& e, int img, int oy, int ox, int c, const float (&v)[16], int cnt) {
   if (e.out_c8) {
     // two channel blocks of 8: 16 B each, one plane (Hout*Wout*8 elements) apart
@@ -179,9 +182,24 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int img, int oy,
     return;
   }
   const size_t opix = ((size_t)img * e.Hout + oy) * e.Wout + ox;
+  if (kFast) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.y) + opix * e.ldo + e.choff + c;
+    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    if (cnt > 8)
+      *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    return;
+  }
   const bool al4 = ((e.ldo | e.choff) & 3) == 0, al8 = ((e.ldo | e.choff) & 7) == 0;
   if (e.out_dt == DT_F32) store_row_f32(reinterpret_cast<float*>(e.y) + opix * e.ldo + e.choff + c, v, cnt, al4);
   else store_row_bf16(reinterpret_cast<__nv_bfloat16*>(e.y) + opix * e.ldo + e.choff + c, v, cnt, al8, al4);
+}
+
+// launch-time test for the minimal-instruction epilogue (see epi_store16<true>)
+__host__ __device__ inline bool epi_fast_ok(const EpiParams& e) {
+  if (e.out_dt != DT_BF16) return false;
+  if (e.out_c8) return true;
+  const int n = (e.epi == EPI_LINEAR) ? e.Cout : (e.Cout >> 1);
+  return ((e.ldo | e.choff) & 7) == 0 && (n % 8) == 0;
 }
 
 constexpr int TC_EPI_GROUPS = 2;                                  // epilogue warps = 4 * groups (each group: 4 warps = 128 lanes)
@@ -211,6 +229,7 @@ __device__ __forceinline__ void epi_fill_constants(float* cst, int n, const floa
 //   linear: out[c] = (acc[c] + b[c]) * scale * colscale[img][c]
 // The 16-column chunks of a tile are dealt round-robin to `nsplit` warp groups (this one is `grp`); nsplit == 1 means
 // this group drains the whole tile (the groups then alternate tiles).
+template <bool kFast>
 __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& e, const float* cst, int cst_n, uint32_t taddr, int img, int nt, bool valid,
                                                  int py, int px, int grp, int nsplit = TC_EPI_GROUPS) {
   const int oy = py * e.osy + e.ooy, ox = px * e.osx + e.oox;
@@ -231,7 +250,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& e, const float
           if (cs != nullptr && i < cnt) sc *= __ldg(cs + cb + i);
           v[i] = (i < cnt) ? (v[i] + cst[cb + i]) * sc : 0.0f;
         }
-        epi_store16(e, img, oy, ox, cb, v, cnt);
+        epi_store16<kFast>(e, img, oy, ox, cb, v, cnt);
       }
     }
   } else {
@@ -273,7 +292,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& e, const float
             f[k] = (k < cnt) ? a * sg : 0.0f;
           }
         }
-        epi_store16(e, img, oy, ox, c0, f, cnt);
+        epi_store16<kFast>(e, img, oy, ox, c0, f, cnt);
       }
     }
   }
