@@ -41,14 +41,19 @@ constexpr int TMEM_COLS = TC_TMEM_COLS;
 constexpr int ACC_STRIDE = TC_ACC_STRIDE;
 constexpr int MAX_STAGES = TC_MAX_STAGES;
 
+// R64 / R32: compile-time copies of p.r64 / p.r32 (R64 < 0: run-time values). Compile-time trip counts let the MMA
+// issue sequence of a k-step unroll completely (a rolled loop is issue-latency bound at ~110 cycles per MMA,
+// tools/bench/mma_rate.cu).
+template <int R64, int R32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmA32, const TcParams p) {
+  const int r64 = R64 >= 0 ? R64 : p.r64, r32 = R64 >= 0 ? R32 : p.r32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A64 x r64 | A32 x r32 | B image] then barriers, tmem ptr, bias
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_bytes = p.r64 * A64_BYTES + p.r32 * A32_BYTES;
+  const int a_bytes = r64 * A64_BYTES + r32 * A32_BYTES;
   const int b64_bytes = p.NT * 128, b32_bytes = p.NT * 64;
-  const int b_bytes = p.r64 * b64_bytes + p.r32 * b32_bytes;
+  const int b_bytes = r64 * b64_bytes + r32 * b32_bytes;
   const int stage_bytes = a_bytes + b_bytes;
   uint8_t* tail = smem + (size_t)p.num_stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -114,14 +119,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
         if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           bulk_load_1d(sA + a_bytes, wsrc + (size_t)ks * b_bytes, (uint32_t)b_bytes, &full_bar[stage]);
-          for (int j = 0; j < p.r64; ++j) {
-            const int u = ks * p.r64 + j;
+          for (int j = 0; j < r64; ++j) {
+            const int u = ks * r64 + j;
             const int t = u / p.n64, chunk = u - t * p.n64;
             tma_load_4d(sA + j * A64_BYTES, &tmA64, &full_bar[stage], chunk * 64, x0 + p.dx[t], y0 + p.dy[t], img);
           }
-          for (int j = 0; j < p.r32; ++j) {
-            const int t = ks * p.r32 + j;     // n32 == 1: one 32-wide unit per tap
-            tma_load_4d(sA + p.r64 * A64_BYTES + j * A32_BYTES, &tmA32, &full_bar[stage], p.n64 * 64, x0 + p.dx[t], y0 + p.dy[t], img);
+          for (int j = 0; j < r32; ++j) {
+            const int t = ks * r32 + j;     // n32 == 1: one 32-wide unit per tap
+            tma_load_4d(sA + r64 * A64_BYTES + j * A32_BYTES, &tmA32, &full_bar[stage], p.n64 * 64, x0 + p.dx[t], y0 + p.dy[t], img);
           }
         }
         __syncwarp();
@@ -133,6 +138,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
     // ==================================================================== MMA issuer (warp converged, one lane issues)
     // instruction descriptor: D=f32, A=B=bf16, K-major both, N = NT, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // shared-window address as a plain integer: uniform
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
@@ -150,33 +156,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
         mbar_wait(&full_bar[stage], phase, 3);
         if (p.dbg) t_wfull += clock64() - tw;
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sA = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t sB = sA + a_bytes;
-        if (elect_one()) {
+        {
+          const uint32_t lead = elect_one() ? 1u : 0u;   // predicated issue: the warp stays converged
           uint32_t acc = ks ? 1u : 0u;
+          const uint32_t hi128 = (1024u >> 4) | (1u << 14) | (2u << 29), hi64 = (512u >> 4) | (1u << 14) | (4u << 29);
           // 64-channel units: four K=16 MMAs each, +32 B (= +2 in the descriptor) per step
-          uint64_t ad = make_kmajor_desc(sA, true), bd = make_kmajor_desc(sB, true);
-          for (int j = 0; j < p.r64; ++j) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, acc);
-              acc = 1u;
+          for (int j = 0; j < (R64 >= 0 ? R64 : 16); ++j) {
+            if (j < r64) {
+              const uint32_t a0 = (sA + j * A64_BYTES) >> 4, b0 = (sB + j * b64_bytes) >> 4;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_if32(lead, tmem_d, a0 + 2 * k, hi128, b0 + 2 * k, hi128, idesc, acc);
+                acc = 1u;
+              }
             }
-            ad += A64_BYTES >> 4;
-            bd += (uint32_t)b64_bytes >> 4;
           }
           // trailing 32-channel units: two K=16 MMAs each
-          ad = make_kmajor_desc(sA + p.r64 * A64_BYTES, false);
-          bd = make_kmajor_desc(sB + p.r64 * b64_bytes, false);
-          for (int j = 0; j < p.r32; ++j) {
-            umma_bf16(tmem_d, ad, bd, idesc, acc);
-            umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
-            acc = 1u;
-            ad += A32_BYTES >> 4;
-            bd += (uint32_t)b32_bytes >> 4;
+#pragma unroll
+          for (int j = 0; j < (R64 >= 0 ? R32 : 16); ++j) {
+            if (j < r32) {
+              const uint32_t a0 = (sA + r64 * A64_BYTES + j * A32_BYTES) >> 4, b0 = (sB + r64 * b64_bytes + j * b32_bytes) >> 4;
+              umma_bf16_if32(lead, tmem_d, a0, hi64, b0, hi64, idesc, acc);
+              umma_bf16_if32(lead, tmem_d, a0 + 2, hi64, b0 + 2, hi64, idesc, 1u);
+              acc = 1u;
+            }
           }
-          umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-          if (ks == ksteps - 1) umma_commit(&tmem_full[as]);    // accumulator complete
+          umma_commit_if(lead, &empty_bar[stage]);                       // smem slot free once these MMAs retire
+          if (ks == ksteps - 1) umma_commit_if(lead, &tmem_full[as]);    // accumulator complete
         }
         __syncwarp();
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -336,6 +345,9 @@ static int encode_act_map(EncodeTiledFn enc, CUtensorMap* tm, const ConvParams& 
   return 0;
 }
 
+// k-step structures used by the generator: stride-2 layers (0,3) (1,0), attention S (1,1) and AV (1,0)
+#define TC_SPECIALISATIONS(X) X(0, 3) X(1, 0) X(1, 1)
+
 int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
   TcParams p;
   int smem_bytes = 0;
@@ -348,7 +360,10 @@ int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
     SE_CUDA_OK(cudaGetDevice(&dev));
     SE_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     SE_CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    SE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+#define X(a, b) SE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+    TC_SPECIALISATIONS(X)
+#undef X
+    SE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<-1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
   }
   SE_REQUIRE(smem_bytes <= g_smem_optin, "shared memory plan exceeds the opt-in limit");
 
@@ -367,7 +382,15 @@ int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream) {
     SE_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 8 * 8 * 1024, stream));
     p.dbg = dbg_buf;
   }
-  conv_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA64, tmA32, p);
+  bool launched = false;
+#define X(a, b)                                                                              \
+  if (!launched && p.r64 == a && p.r32 == b) {                                                \
+    conv_tc_kernel<a, b><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA64, tmA32, p);        \
+    launched = true;                                                                          \
+  }
+  TC_SPECIALISATIONS(X)
+#undef X
+  if (!launched) conv_tc_kernel<-1, 0><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA64, tmA32, p);
   SE_CUDA_OK(cudaGetLastError());
   if (dbg_on) {
     SE_CUDA_OK(cudaStreamSynchronize(stream));

@@ -237,7 +237,43 @@ __global__ void plane_reduce_c8_kernel(const __nv_bfloat16* __restrict__ x, int 
 
 // NHWC bf16 with C % 8 == 0: blocks over (pixel slices, image); partial results combined with float atomics
 // (max: order-free; sums: used for the L2 norm only where the bf16 path tolerates re-association)
+// NHWC bf16 sum-of-squares over slices of the plane: partial sums combined with atomicAdd (used for the attention
+// key norm only; re-association is far below bf16 resolution), then 1/sqrt(sum + 1e-8)
+__global__ void plane_sumsq_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int C, int HW, int slices, float* __restrict__ acc) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y, sl = blockIdx.z;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int p0 = (int)((long long)HW * sl / slices), p1 = (int)((long long)HW * (sl + 1) / slices);
+  float a = 0.0f;
+  if (c < C) {
+    const __nv_bfloat16* xp = x + (size_t)b * HW * ldx + c;
+    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+      const float v = __bfloat162float(xp[(size_t)p * ldx]);
+      a = fmaf(v, v, a);
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) a += red[j][threadIdx.x];
+    atomicAdd(acc + (size_t)b * C + c, a);
+  }
+}
+__global__ void rnorm_finalize_kernel(float* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = 1.0f / sqrtf(v[i] + 1e-8f);
+}
+
 int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int c8, int mode, float* out, cudaStream_t s) {
+  if (!c8 && dt == DT_BF16 && mode == RED_RNORM && HW >= 1024) {
+    const int slices = 16;
+    SE_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)B * C * 4, s));
+    dim3 grid(cdiv(C, 32), B, slices), block(32, 8);
+    plane_sumsq_nhwc_kernel<<<grid, block, 0, s>>>((const __nv_bfloat16*)x, ldx, C, HW, slices, out);
+    rnorm_finalize_kernel<<<cdiv((long long)B * C, 256), 256, 0, s>>>(out, B * C);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (c8 && dt == DT_BF16) {
     dim3 grid((C + 7) / 8, B);
     plane_reduce_c8_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, C, HW, mode, out);
@@ -271,7 +307,25 @@ __global__ void broadcast_kernel(const float* __restrict__ v, T* __restrict__ y,
   y[pix * ldo + choff + c] = from_f<T>(v[b * C + c]);
 }
 
+__global__ void broadcast_c8_kernel(const float* __restrict__ v, __nv_bfloat16* __restrict__ y, int C, int HW, int ldo, int choff, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // (b, cb, p)
+  if (i >= total) return;
+  const long long p = i % HW;
+  long long r = i / HW;
+  const int cb = (int)(r % (C >> 3));
+  const long long b = r / (C >> 3);
+  const float* src = v + b * C + cb * 8;
+  const uint4 q = make_uint4(pack_bf16x2(src[0], src[1]), pack_bf16x2(src[2], src[3]), pack_bf16x2(src[4], src[5]), pack_bf16x2(src[6], src[7]));
+  *reinterpret_cast<uint4*>(y + ((b * ldo + (choff >> 3) + cb) * HW + p) * 8) = q;
+}
+
 int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, int c8, cudaStream_t s) {
+  if (c8 && dt == DT_BF16 && C % 8 == 0 && choff % 8 == 0) {
+    const long long n = (long long)B * (C >> 3) * HW;
+    broadcast_c8_kernel<<<cdiv(n, 256), 256, 0, s>>>(v, (__nv_bfloat16*)y, C, HW, ldo, choff, n);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const long long total = (long long)B * HW * C;
   SE_REQUIRE(!c8 || (C % 8 == 0 && choff % 8 == 0), "C8 broadcast needs whole channel blocks");
   SE_DISPATCH_T(dt, (broadcast_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(v, (T*)y, C, HW, ldo, choff, c8, total)));
