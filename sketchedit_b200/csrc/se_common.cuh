@@ -95,7 +95,12 @@ struct EpiParams {
   float scale;
   const float* colscale;
   int Cout, NT;
+  int goff;   // gated epilogues: accumulator column of gate channel 0 (= Cout/2 rounded up to 8; the weight image
+              // places feature c at column c and its gate at goff + c, columns in between are zero weights)
 };
+// column of output channel n in the B (weight) image / accumulator of a gated layer
+inline int gated_goff(int Cout) { return ((Cout / 2) + 7) / 8 * 8; }
+inline int gated_column(int Cout, int n) { const int half = Cout / 2; return n < half ? n : gated_goff(Cout) + (n - half); }
 
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -46,15 +46,23 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, bool sw128) 
 // With compile-time trip counts the MMA issue sequence of a k-step is fully unrolled, so descriptor arithmetic of
 // later MMAs overlaps the (long) issue latency of earlier ones: tools/bench/mma_rate.cu measures ~110 cycles per
 // MMA for a rolled loop against the 40-96 cycle pipe time, i.e. a rolled loop starves the tensor core.
-template <int R64, int R32, int MMAS>
+//
+// PAIR = 1: the CTAs of a 2-CTA cluster work as one cta_group::2 unit on two tiles at a time (M = 256): every CTA
+// loads the halo of ITS tile but only HALF of each weight stage (rows [rank*NT/2, +NT/2) through the 2-D tensor map
+// tmB over the pair-format image), which halves the streamed-weight ingest that bounds the 96->192 layers, and the
+// leader issues one MMA for both tiles. Streaming (non-resident) layers only.
+template <int R64, int R32, int MMAS, int PAIR>
 __global__ void __launch_bounds__(TC_NUM_THREADS, 1)
-conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
+conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const C8Params p) {
+  constexpr bool kPair = PAIR != 0;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const int r64 = R64 >= 0 ? R64 : p.r64, r32 = R64 >= 0 ? R32 : p.r32, mmas64 = R64 >= 0 ? MMAS : p.mmas64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // carve: [halo A buffers][resident weights][stages: (tap A box) + (B image)] [barriers][tmem ptr][bias]
   const bool halo = (p.mode == C8_HALO);
-  const int b64_bytes = p.NT * 128, b32_bytes = p.NT * 64;
+  const int NTl = kPair ? p.NT / 2 : p.NT;                   // B rows held by this CTA
+  const int b64_bytes = NTl * 128, b32_bytes = NTl * 64;
   const int b_bytes = r64 * b64_bytes + r32 * b32_bytes;
   const int stage_a = halo ? 0 : p.a_bytes;
   const int stage_b = p.resident ? 0 : b_bytes;
@@ -66,8 +74,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
   uint64_t* a_full = empty_bar + TC_MAX_STAGES;
-  uint64_t* a_empty = a_full + 2;
-  uint64_t* tmem_full = a_empty + 2;
+  uint64_t* a_empty = a_full + C8_MAX_ABUFS;
+  uint64_t* tmem_full = a_empty + C8_MAX_ABUFS;
   uint64_t* tmem_empty = tmem_full + 4;
   uint64_t* wres_bar = tmem_empty + 4;
   // accumulator ring: N <= 128 leaves room for 4 TMEM stages; the two epilogue groups then drain alternate tiles
@@ -87,25 +95,30 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C8_MAX_ABUFS; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128 * epi_split);
+      mbar_init(&tmem_empty[i], kPair ? 2 * 4 * epi_split : 128 * epi_split);   // pair: one arrive per epilogue warp of both CTAs
     }
     mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   const int cst_n = p.NT + 32;
-  epi_fill_constants(bias_s, cst_n, p.bias, p.e.Cout, threadIdx.x, TC_NUM_THREADS);
+  epi_fill_constants(bias_s, cst_n, p.bias, p.e, threadIdx.x, TC_NUM_THREADS);
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();       // pair: the peer's barriers must exist before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -139,14 +152,20 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
       }
       const int x0 = tx * C8_TW, y0 = ty * C8_TH;
       if (halo) {
-        const int ab = (p.a_bufs == 2) ? (iter & 1) : 0;               // no integer division: keeps the value uniform
-        const uint32_t aphase = (p.a_bufs == 2) ? ((iter >> 1) & 1) : (iter & 1);
+        const int ab = iter & (p.a_bufs - 1);                          // power-of-two ring, no integer division: stays uniform
+        const uint32_t aphase = (iter >> p.a_shift) & 1;
         const long long tw = p.dbg ? clock64() : 0;
         mbar_wait(&a_empty[ab], aphase ^ 1, 5);
         if (p.dbg) t_wait += clock64() - tw;
         if (elect_one()) {
-          mbar_expect_tx(&a_full[ab], (uint32_t)p.a_tx_bytes);
-          tma_load_4d(sHalo + (size_t)ab * p.a_bytes, &tmA, &a_full[ab], (x0 - p.pad_x0) * 8, y0 - p.pad_y0, p.x_cb_off, img);
+          if (kPair) {
+            if (cta_rank == 0) mbar_expect_tx(&a_full[ab], 2u * (uint32_t)p.a_tx_bytes);
+            tma_load_4d_pair(sHalo + (size_t)ab * p.a_bytes, &tmA, mapa_rank(smem_u32(&a_full[ab]), 0), (x0 - p.pad_x0) * 8, y0 - p.pad_y0,
+                             p.x_cb_off, img);
+          } else {
+            mbar_expect_tx(&a_full[ab], (uint32_t)p.a_tx_bytes);
+            tma_load_4d(sHalo + (size_t)ab * p.a_bytes, &tmA, &a_full[ab], (x0 - p.pad_x0) * 8, y0 - p.pad_y0, p.x_cb_off, img);
+          }
         }
         __syncwarp();
       }
@@ -157,10 +176,17 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
           if (p.dbg) t_wait += clock64() - tw;
           uint8_t* st = sStages + (size_t)stage * stage_bytes;
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
-            if (!p.resident) bulk_load_1d(st + stage_a, p.w + (size_t)ks * b_bytes, (uint32_t)b_bytes, &full_bar[stage]);
-            if (!halo) {   // PERTAP: a stage is exactly one tap
-              tma_load_4d(st, &tmA, &full_bar[stage], (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off, img);
+            if (kPair) {
+              const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
+              tma_load_2d_pair(st + stage_a, &tmB, lead_bar, 0, (ks * 2 + (int)cta_rank) * (b_bytes >> 7));
+              if (!halo) tma_load_4d_pair(st, &tmA, lead_bar, (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off, img);
+            } else {
+              mbar_expect_tx(&full_bar[stage], (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
+              if (!p.resident) bulk_load_1d(st + stage_a, p.w + (size_t)ks * b_bytes, (uint32_t)b_bytes, &full_bar[stage]);
+              if (!halo) {   // PERTAP: a stage is exactly one tap
+                tma_load_4d(st, &tmA, &full_bar[stage], (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off, img);
+              }
             }
           }
           __syncwarp();
@@ -169,9 +195,15 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
       }
     }
     if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
-  } else if (warp == 1) {
-    // ==================================================================== MMA issuer
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  } else if ((warp == 1 || (warp == 3 && !staged)) && (!kPair || cta_rank == 0)) {
+    // ==================================================================== MMA issuer (pair: the leader, for both CTAs)
+    // Nothing streamed per k-step (resident weights + halo): a tile is ONE short burst of MMAs, and the issuer's
+    // per-tile protocol (two commits, two barrier waits, fence, descriptor set-up: ~600 cycles measured) is longer
+    // than the 3-4 queued MMAs of a small-N layer (40-56 cycles each) can cover, so the tensor pipe would idle
+    // between tiles. Warps 1 and 3 therefore issue alternate tiles: each one's protocol overlaps the other's burst.
+    const bool dual = !staged;
+    const int me = (warp == 3) ? 1 : 0;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
     int stage = 0, iter = 0;
     uint32_t phase = 0;
     long long t_wfull = 0, t_wtmem = 0, t_begin = clock64();
@@ -180,15 +212,16 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
     const uint32_t off_stages = off_wres + (p.resident ? (uint32_t)p.wres_bytes : 0u);
     if (p.resident) mbar_wait(wres_bar, 0, 6);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      if (dual && (iter & 1) != me) continue;
       const int as = iter & (acc_stages - 1);
       const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
       long long tw = p.dbg ? clock64() : 0;
-      mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
+      if (kPair) mbar_wait_cluster(&tmem_empty[as], accphase ^ 1, 2); else mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
       if (p.dbg) t_wtmem += clock64() - tw;
-      const int ab = (halo && p.a_bufs == 2) ? (iter & 1) : 0;
+      const int ab = halo ? (iter & (p.a_bufs - 1)) : 0;
       if (halo) {
         tw = p.dbg ? clock64() : 0;
-        mbar_wait(&a_full[ab], (p.a_bufs == 2) ? ((iter >> 1) & 1) : (iter & 1), 7);
+        mbar_wait(&a_full[ab], (iter >> p.a_shift) & 1, 7);
         if (p.dbg) t_wfull += clock64() - tw;
       }
       tc_fence_after();
@@ -223,7 +256,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < mmas64) {
-                  umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+                  if (kPair) umma2_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+                  else umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
                   acc = 1u;
                 }
               }
@@ -236,22 +270,31 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
               const uint32_t b0 = (sB + r64 * b64_bytes + j * b32_bytes) >> 4;
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
-                umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
+                if (kPair) umma2_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
+                else umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
                 acc = 1u;
               }
             }
           }
-          if (staged) umma_commit_if(lead, &empty_bar[stage]);
-          if (ks == ksteps - 1) {
-            if (halo) umma_commit_if(lead, &a_empty[ab]);
-            umma_commit_if(lead, &tmem_full[as]);
+          if (kPair) {
+            if (staged) umma2_commit_if(lead, &empty_bar[stage]);
+            if (ks == ksteps - 1) {
+              if (halo) umma2_commit_if(lead, &a_empty[ab]);
+              umma2_commit_if(lead, &tmem_full[as]);
+            }
+          } else {
+            if (staged) umma_commit_if(lead, &empty_bar[stage]);
+            if (ks == ksteps - 1) {
+              if (halo) umma_commit_if(lead, &a_empty[ab]);
+              umma_commit_if(lead, &tmem_full[as]);
+            }
           }
         }
         __syncwarp();
         if (staged && ++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
-    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
+    if (p.dbg && lane == 0 && warp == 1) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
   } else if (warp >= 4) {
     // ==================================================================== epilogue
     const int q = warp & 3;
@@ -270,7 +313,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
         if (ty >= p.tiles_y) { ty -= p.tiles_y; ++img; }
         img += p.step_img;
       }
-      if (epi_split == 1 && (iter & 1) != grp) continue;      // tile-alternating groups
+      if (epi_split == 1 && (iter & (TC_EPI_GROUPS - 1)) != grp) continue;      // tile-alternating groups
       const int as = iter & (acc_stages - 1);
       const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
       const long long tw = p.dbg ? clock64() : 0;
@@ -283,16 +326,22 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const C8Params p) {
       if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
       else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if (kPair) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0));   // the leader's MMA warp owns both accumulators
+      } else {
+        mbar_arrive(&tmem_empty[as]);
+      }
     }
     if (p.dbg && threadIdx.x == 128) { p.dbg[blockIdx.x * 8 + 5] = t_wacc; p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin; }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();       // pair: no CTA may exit while its peer still reads its shared memory
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -338,7 +387,7 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
   // so the MMAs never multiply stale shared memory (possibly NaN bit patterns) by the zero weight columns
   L->cb_in = stem ? 1 : (w.n64 * 64 + w.n32 * 32) / 8;
   const long long halo_bytes = (long long)L->cb_in * HR * WR * 16;
-  w.NT = (Cout + 15) / 16 * 16;
+  w.NT = (gated_goff(Cout) + Cout / 2 + 15) / 16 * 16;   // every layer on this path is gated: gate columns start at goff
   w.n_tiles = 1;
   w.img_bytes = 0;
   const long long wbytes = (long long)ntaps * w.NT * (w.n64 * 128 + w.n32 * 64);
@@ -372,22 +421,61 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
 
 // the k-step structures of the generator's layers get their own fully unrolled instantiation
 #define C8_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(1, 0, 4) X(1, 1, 4) X(4, 4, 4) X(4, 0, 4) X(0, 3, 4) X(0, 1, 4)
+// k-step structures of the streamed-weight layers that run as CTA pairs (96->192: <1,1>; 192/48/384->192: <1,0>)
+#define C8_PAIR_SPECIALISATIONS(X) X(1, 0, 4) X(1, 1, 4)
 static int c8_set_smem_attr(int bytes) {
-#define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   C8_SPECIALISATIONS(X)
 #undef X
-  SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<-1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  C8_PAIR_SPECIALISATIONS(X)
+#undef X
+  SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<-1, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return 0;
 }
-static void c8_dispatch(const C8Params& p, const CUtensorMap& tmA, int grid, int smem_bytes, cudaStream_t stream) {
+static bool c8_pair_kernel_exists(int r64, int r32, int mmas64) {
+#define X(a, b, m) if (r64 == a && r32 == b && mmas64 == m) return true;
+  C8_PAIR_SPECIALISATIONS(X)
+#undef X
+  return false;
+}
+static int c8_dispatch(const C8Params& p, const CUtensorMap& tmA, const CUtensorMap& tmB, bool pair, int grid, int smem_bytes,
+                       cudaStream_t stream) {
+  if (pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_NUM_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+#define X(a, b, m)                                                                             \
+    if (p.r64 == a && p.r32 == b && p.mmas64 == m) {                                            \
+      SE_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_c8_kernel<a, b, m, 1>, tmA, tmB, p));            \
+      return 0;                                                                                \
+    }
+    C8_PAIR_SPECIALISATIONS(X)
+#undef X
+    SE_REQUIRE(false, "no CTA-pair instantiation for this k-step structure");
+  }
 #define X(a, b, m)                                                                             \
   if (p.r64 == a && p.r32 == b && (a == 0 || p.mmas64 == m)) {                                 \
-    conv_c8_kernel<a, b, m><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, p);             \
-    return;                                                                                    \
+    conv_c8_kernel<a, b, m, 0><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);     \
+    return 0;                                                                                  \
   }
   C8_SPECIALISATIONS(X)
 #undef X
-  conv_c8_kernel<-1, 0, 0><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, p);
+  conv_c8_kernel<-1, 0, 0, 0><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  return 0;
+}
+
+// may this layer run as CTA pairs? (decided at packing time: the pair-format weight image is built only then)
+bool c8_pair_capable(const C8Layer& L) {
+  static const bool off = getenv("SE_C8_NOPAIR") != nullptr;
+  const TcWeights& w = L.w;
+  if (off || L.resident || L.stem || w.NT % 32 != 0) return false;
+  const int rows_half = (w.NT / 2) * (w.r64 * 128 + w.r32 * 64) / 128;
+  return rows_half <= 256 && c8_pair_kernel_exists(w.n64 ? w.r64 : 0, w.n32 ? w.r32 : 0, 4);
 }
 
 int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
@@ -435,19 +523,26 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   SE_REQUIRE(c.epi == EPI_LINEAR || (c.Cout % 2 == 0 && c.out_dt == DT_BF16), "gated epilogue needs even Cout, bf16 out");
   SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
 
-  const int b_bytes = tc_stage_b_bytes(w);
+  const int total_tiles = p.N * p.tiles_x * p.tiles_y;
+  const bool pair = L.w_pair != nullptr && total_tiles % 2 == 0;
+  const int b_bytes = pair ? tc_stage_b_bytes(w) / 2 : tc_stage_b_bytes(w);   // per CTA
   const int stage_bytes = (L.mode == C8_HALO ? 0 : L.a_bytes) + (L.resident ? 0 : b_bytes);
   int fixed = (L.resident ? p.wres_bytes : 0);
   p.a_bufs = 2;
   if (L.mode == C8_HALO) {
     if (fixed + 2 * L.a_bytes + 3 * stage_bytes > kSmemBudget) p.a_bufs = 1;   // measured: 2 halo buffers + 3 weight stages beats 1 + 4
+    // nothing streamed: a tile is short (700-2000 cycles of MMAs) against a TMA round trip of ~1500 cycles, so two
+    // halo buffers leave the tensor pipe waiting for loads; ring as deep as shared memory allows (power of two)
+    if (stage_bytes == 0)
+      while (p.a_bufs < C8_MAX_ABUFS && fixed + 2 * p.a_bufs * L.a_bytes <= kSmemBudget) p.a_bufs *= 2;
     fixed += p.a_bufs * L.a_bytes;
   }
+  for (p.a_shift = 0; (1 << p.a_shift) < p.a_bufs; ++p.a_shift) {}
   int stages = stage_bytes ? (kSmemBudget - fixed) / stage_bytes : 1;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SE_REQUIRE(stages >= (stage_bytes ? 2 : 1), "shared memory plan does not fit");
   p.num_stages = stages;
-  const int smem_bytes = 1024 + fixed + stages * stage_bytes + (2 * TC_MAX_STAGES + 13) * 8 + 16 + 3 * (p.NT + 32) * 4 + 64;
+  const int smem_bytes = 1024 + fixed + stages * stage_bytes + (2 * TC_MAX_STAGES + 2 * C8_MAX_ABUFS + 9) * 8 + 16 + 3 * (p.NT + 32) * 4 + 64;
 
   EncodeTiledFn enc = c8_encode_fn();
   SE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
@@ -472,8 +567,22 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(C8) failed, CUresult=" + std::to_string((int)r));
   }
-  const int total_tiles = p.N * p.tiles_x * p.tiles_y;
-  const int grid = total_tiles < g_sms ? total_tiles : g_sms;
+  CUtensorMap tmB;
+  memset(&tmB, 0, sizeof(tmB));
+  if (pair) {
+    // pair-format weights as 128 B rows: stage ks = [rank 0 half][rank 1 half], one box per (stage, rank)
+    const int rows_half = b_bytes / 128;
+    cuuint64_t dims[2] = {64, (cuuint64_t)p.ksteps * 2 * rows_half};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)rows_half};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(L.w_pair), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(pair weights) failed, CUresult=" + std::to_string((int)r));
+  }
+  int grid = total_tiles < g_sms ? total_tiles : g_sms;
+  if (pair) grid &= ~1;
   p.step_x = grid % p.tiles_x;
   p.step_y = (grid / p.tiles_x) % p.tiles_y;
   p.step_img = grid / (p.tiles_x * p.tiles_y);
@@ -484,7 +593,7 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
     SE_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 8 * 8 * 1024, stream));
     p.dbg = dbg_buf;
   }
-  c8_dispatch(p, tmA, grid, smem_bytes, stream);
+  { int rc_launch = c8_dispatch(p, tmA, tmB, pair, grid, smem_bytes, stream); if (rc_launch) return rc_launch; }
   SE_CUDA_OK(cudaGetLastError());
   if (dbg_on) {
     SE_CUDA_OK(cudaStreamSynchronize(stream));
@@ -494,8 +603,8 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
     for (int b = 0; b < grid; ++b)
       for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 8 + k] / grid;
     fprintf(stderr,
-            "[c8] N=%d %dx%d Ci=%d taps=%d NT=%d mode=%s res=%d HRxWR=%dx%d abufs=%d n64=%d n32=%d r64=%d r32=%d stages=%d tiles=%d | prod wait %.0f/%.0f | mma wait_full %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f\n",
-            c.N, c.Ho, c.Wo, c.Ci, c.ntaps, p.NT, L.mode == C8_HALO ? "halo" : "pertap", p.resident, L.HR, L.WR, p.a_bufs, p.n64, p.n32, p.r64, p.r32,
+            "[c8] N=%d %dx%d Ci=%d taps=%d NT=%d mode=%s pair=%d res=%d HRxWR=%dx%d abufs=%d n64=%d n32=%d r64=%d r32=%d stages=%d tiles=%d | prod wait %.0f/%.0f | mma wait_full %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f\n",
+            c.N, c.Ho, c.Wo, c.Ci, c.ntaps, p.NT, L.mode == C8_HALO ? "halo" : "pertap", (int)pair, p.resident, L.HR, L.WR, p.a_bufs, p.n64, p.n32, p.r64, p.r32,
             p.num_stages, total_tiles, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
   }
   return 0;

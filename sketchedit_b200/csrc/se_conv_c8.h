@@ -6,6 +6,7 @@
 namespace se {
 
 enum { C8_HALO = 0, C8_PERTAP = 1 };
+constexpr int C8_MAX_ABUFS = 8;   // halo ring depth (resident layers)
 constexpr int C8_MAX_UNITS = 64;   // (tap, channel chunk) K units per tile
 
 // per-layer (per sub-pixel class) configuration fixed at weight-packing time
@@ -18,6 +19,7 @@ struct C8Layer {
   int HR = 0, WR = 0;   // rows / columns of the shared-memory A region
   int pad_y0 = 0, pad_x0 = 0;
   int a_bytes = 0, a_tx_bytes = 0;
+  const void* w_pair = nullptr;   // CTA-pair format of the stage images (each stage = [rows 0..NT/2) | rows NT/2..NT)), or null
 };
 
 struct C8Params {
@@ -29,7 +31,7 @@ struct C8Params {
   int n64, n32, r64, r32, NT, ksteps;
   const uint8_t* w;
   int mode, HR, WR, pad_y0, pad_x0, cb_in, x_cb_off;
-  int a_bytes, a_tx_bytes, a_bufs;
+  int a_bytes, a_tx_bytes, a_bufs, a_shift;   // halo ring: a_bufs = 1 << a_shift buffers
   int lbo_bytes, sbo_bytes, kstep_bytes, mmas64;
   uint32_t aoff[C8_MAX_UNITS];   // byte offset of each K unit's A operand inside the shared-memory region
   int num_stages, resident, wres_bytes;
@@ -39,6 +41,13 @@ struct C8Params {
 };
 
 int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem);
+bool c8_pair_capable(const C8Layer& L);
+// byte offset of element (unit, n, k) of a stage in the CTA-pair image: the two row halves are separate sub-images
+inline uint32_t c8_pair_image_offset(const TcWeights& w, bool is64, int j, int n, int k) {
+  const int NTh = w.NT / 2;
+  const uint32_t half_bytes = (uint32_t)NTh * (w.r64 * 128 + w.r32 * 64);
+  return (uint32_t)(n / NTh) * half_bytes + tc_b_image_offset(NTh, w.n64 ? w.r64 : 0, is64, j, n % NTh, k);
+}
 int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream);
 
 }  // namespace se

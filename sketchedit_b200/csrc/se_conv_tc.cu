@@ -87,7 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
   }
   // bias (all N tiles) into shared memory; zero when absent
   const int cst_n = p.n_tiles * p.NT + 32;
-  epi_fill_constants(bias_s, cst_n, p.bias, p.e.Cout, threadIdx.x, NUM_THREADS);
+  epi_fill_constants(bias_s, cst_n, p.bias, p.e, threadIdx.x, NUM_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -287,6 +287,7 @@ void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
   e->osy = c.osy; e->ooy = c.ooy; e->osx = c.osx; e->oox = c.oox;
   e->epi = c.epi; e->scale = c.scale; e->colscale = c.colscale;
   e->Cout = c.Cout; e->NT = NT;
+  e->goff = (c.epi == EPI_LINEAR) ? 0 : gated_goff(c.Cout);
 }
 
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes) {

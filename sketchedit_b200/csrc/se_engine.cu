@@ -219,7 +219,7 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
       int rem = Ci - 64 * tc.n64;
       if (rem > 32) { ++tc.n64; rem = 0; }
       tc.n32 = rem > 0 ? 1 : 0;
-      tc.NT = (Cout + 15) / 16 * 16;
+      tc.NT = (gated_goff(Cout) + Cout / 2 + 15) / 16 * 16;   // gate columns start at goff (se_common.cuh: gated_column)
       tc.n_tiles = 1;
       tc.img_bytes = 0;
       tc_choose_stage(&tc);
@@ -235,18 +235,39 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
       for (int j = 0; j < tc.r64 && tc.n64; ++j) {
         const int u = ks * tc.r64 + j, t = u / tc.n64, chunk = u % tc.n64;
         for (int n = 0; n < Cout; ++n)
-          for (int k = 0; k < 64; ++k) base[tc_b_image_offset(tc.NT, tc.r64, true, j, n, k) / 2] = wv(t, chunk * 64 + k, n);
+          for (int k = 0; k < 64; ++k) base[tc_b_image_offset(tc.NT, tc.r64, true, j, gated_column(Cout, n), k) / 2] = wv(t, chunk * 64 + k, n);
       }
       for (int j = 0; j < tc.r32 && tc.n32; ++j) {
         const int t = ks * tc.r32 + j;
         for (int n = 0; n < Cout; ++n)
-          for (int k = 0; k < 32; ++k) base[tc_b_image_offset(tc.NT, tc.n64 ? tc.r64 : 0, false, j, n, k) / 2] = wv(t, tc.n64 * 64 + k, n);
+          for (int k = 0; k < 32; ++k) base[tc_b_image_offset(tc.NT, tc.n64 ? tc.r64 : 0, false, j, gated_column(Cout, n), k) / 2] = wv(t, tc.n64 * 64 + k, n);
       }
     }
     void* d = nullptr;
     int rc = upload(m, img.data(), img.size() * 2, &d);
     if (rc) return rc;
     tc.data = d;
+    if (cw.use_c8 && c8_pair_capable(cw.c8)) {
+      // second copy in CTA-pair format (se_conv_c8.cu, PAIR = 1): each CTA of a pair streams only its half of the rows
+      std::fill(img.begin(), img.end(), (uint16_t)0);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        uint16_t* base = img.data() + (size_t)ks * sb / 2;
+        for (int j = 0; j < tc.r64 && tc.n64; ++j) {
+          const int u = ks * tc.r64 + j, t = u / tc.n64, chunk = u % tc.n64;
+          for (int n = 0; n < Cout; ++n)
+            for (int k = 0; k < 64; ++k) base[c8_pair_image_offset(tc, true, j, gated_column(Cout, n), k) / 2] = wv(t, chunk * 64 + k, n);
+        }
+        for (int j = 0; j < tc.r32 && tc.n32; ++j) {
+          const int t = ks * tc.r32 + j;
+          for (int n = 0; n < Cout; ++n)
+            for (int k = 0; k < 32; ++k) base[c8_pair_image_offset(tc, false, j, gated_column(Cout, n), k) / 2] = wv(t, tc.n64 * 64 + k, n);
+        }
+      }
+      void* dp = nullptr;
+      rc = upload(m, img.data(), img.size() * 2, &dp);
+      if (rc) return rc;
+      cw.c8.w_pair = dp;
+    }
   }
   return 0;
 }

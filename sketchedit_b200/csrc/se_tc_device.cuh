@@ -35,6 +35,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   __trap();
 }
 
+// same, acquiring at cluster scope: the barrier is signalled by threads of the peer CTA (CTA pairs)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("se_conv_c8: cluster mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
+
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -101,6 +119,64 @@ __device__ __forceinline__ void umma_commit_if(uint32_t lead, uint64_t* bar) {
       : "memory");
 }
 
+// ------------------------------------------------------------------------------------------ CTA pairs (cta_group::2)
+// Two CTAs of a cluster (one TPC) execute ONE M=256 MMA: each supplies its own 128 rows of A and HALF of the B rows
+// from its own shared memory (same offsets in both CTAs), accumulators land in each CTA's own TMEM. Only the
+// leader (cluster rank 0) issues; TMA loads of both CTAs complete on the LEADER's mbarrier, commits are multicast.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `bar` (a local shared::cta address) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// loads into OWN shared memory, completion bytes signalled on a (possibly remote) barrier of the CTA pair
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_if32(uint32_t lead, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma2_commit_if(uint32_t lead, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(lead)
+      : "memory");
+}
+
 // mbarrier arrives once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -115,6 +191,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 // must be executed before the registers written by tmem_ld16 are read
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -160,7 +244,15 @@ __device__ __forceinline__ void store_row_f32(float* o, const float (&r)[16], in
 }
 
 
-constexpr int TC_NUM_THREADS = 128 + 128 * 2;   // 4 role warps + 2 epilogue groups of 4 warps (== TC_THREADS below)
+#ifndef SE_EPI_GROUPS
+#define SE_EPI_GROUPS 4
+#endif
+// Epilogue warps = 4 * groups (a group = 4 warps = the 128 TMEM lanes). The fused epilogue is latency bound (MUFU
+// and TMEM-load dependency chains), so it wants warps, not ILP: with 2 groups (2 warps per scheduler) ncu shows the
+// epilogue warps issuing on ~19 % of their cycles; 4 groups double the warps hiding each other's latencies. 640
+// threads cap the kernel at 96 registers per thread.
+constexpr int TC_EPI_GROUPS = SE_EPI_GROUPS;
+constexpr int TC_NUM_THREADS = 128 + 128 * TC_EPI_GROUPS;   // 4 role warps + the epilogue groups (== TC_THREADS below)
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_ACC_STRIDE = 256;   // TMEM columns between the two accumulator stages
 constexpr int TC_MAX_STAGES = 8;
@@ -194,7 +286,8 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int img, int oy,
   else store_row_bf16(reinterpret_cast<__nv_bfloat16*>(e.y) + opix * e.ldo + e.choff + c, v, cnt, al8, al4);
 }
 
-// launch-time test for the minimal-instruction epilogue (see epi_store16<true>)
+// launch-time test for the minimal-instruction epilogue: bf16 output written as whole 16 B channel blocks
+// (C8, or NHWC with 16 B aligned pixel rows and a channel count that is a multiple of 8)
 __host__ __device__ inline bool epi_fast_ok(const EpiParams& e) {
   if (e.out_dt != DT_BF16) return false;
   if (e.out_c8) return true;
@@ -202,9 +295,8 @@ __host__ __device__ inline bool epi_fast_ok(const EpiParams& e) {
   return ((e.ldo | e.choff) & 7) == 0 && (n % 8) == 0;
 }
 
-constexpr int TC_EPI_GROUPS = 2;                                  // epilogue warps = 4 * groups (each group: 4 warps = 128 lanes)
 constexpr int TC_EPI_THREADS = 128 * TC_EPI_GROUPS;
-constexpr int TC_THREADS = 128 + TC_EPI_THREADS;                   // warps 0-3: producer / MMA / TMEM alloc / spare
+constexpr int TC_THREADS = 128 + TC_EPI_THREADS;                   // warps 0-3: producer / MMA / TMEM alloc / 2nd MMA issuer
 
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
@@ -212,20 +304,104 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
-// Epilogue constants in shared memory, three float arrays of `n` entries each:
+// Epilogue constants in shared memory, three float arrays of `n` entries each, indexed by ACCUMULATOR COLUMN:
 //   [0,n)  bias b    [n,2n)  b * log2(e) (ELU exponent)    [2n,3n)  0.5 * b (sigmoid-as-tanh argument)
-__device__ __forceinline__ void epi_fill_constants(float* cst, int n, const float* bias, int Cout, int tid, int nthreads) {
+// (gated layers: column c = feature c, column goff + c = its gate; see gated_column)
+__device__ __forceinline__ void epi_fill_constants(float* cst, int n, const float* bias, const EpiParams& e, int tid, int nthreads) {
+  const int half = e.Cout >> 1;
   for (int i = tid; i < n; i += nthreads) {
-    const float b = (bias != nullptr && i < Cout) ? bias[i] : 0.0f;
+    int ch = i;   // output channel held by column i (-1: padding column)
+    if (e.epi != EPI_LINEAR) ch = i < half ? i : (i >= e.goff && i < e.goff + half ? half + i - e.goff : -1);
+    const float b = (bias != nullptr && ch >= 0 && ch < e.Cout) ? bias[ch] : 0.0f;
     cst[i] = b;
     cst[n + i] = b * 1.4426950408889634f;
     cst[2 * n + i] = 0.5f * b;
   }
 }
 
+// one gated output: act(f + b) * sigmoid(g + b')  (reference utils.py:29-32)
+//   sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 (one MUFU); ELU's exp as ex2 with the bias folded into the FMA
+template <bool kElu>
+__device__ __forceinline__ float gate_one(float f, float g, float b, float bl, float hb) {
+  const float fv = f + b;
+  float a;
+  if (kElu) {
+    const float ex = ex2_approx(fmaf(f, 1.4426950408889634f, bl)) - 1.0f;
+    a = fv > 0.0f ? fv : ex;
+  } else {
+    a = fmaxf(fv, 0.0f);
+  }
+  const float h = 0.5f * a;
+  return fmaf(h, tanh_approx(fmaf(g, 0.5f, hb)), h);
+}
+
+// Gated epilogue of one accumulator tile, minimal-instruction form (epi_fast_ok): work is cut in 8-column channel
+// blocks (= one 16 B store); no masking is needed because padding columns hold zero weights and zero bias, so they
+// come out as act(0) * sigmoid(0) = 0, which is exactly what the C8 padding channels must contain.
+// nsplit == 1: this group drains the whole tile (16 columns at a time, 8 for an odd last block);
+// nsplit  > 1: the blocks are dealt to the groups, 16 columns at a time if that divides evenly, else 8.
+template <bool kElu>
+__device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const float* cst, int cst_n, uint32_t taddr, int img, bool valid,
+                                                       int oy, int ox, int grp, int nsplit) {
+  const int half = e.Cout >> 1, goff = e.goff;
+  const int nb = (half + 7) >> 3;
+  const uint32_t cs0 = smem_u32(cst);
+  __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(e.y);
+  size_t ostep;   // elements between consecutive 8-channel blocks of this pixel
+  if (e.out_c8) {
+    ostep = (size_t)e.Hout * e.Wout * 8;
+    obase += (((size_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout * 8 + (size_t)ox * 8;
+  } else {
+    ostep = 8;
+    obase += (((size_t)img * e.Hout + oy) * e.Wout + ox) * e.ldo + e.choff;
+  }
+  // 4 outputs [c, c+4) from f[k..k+3], g[k..k+3]
+  auto gate4 = [&](float* f, const float* g, int c, int k) {
+    const float4 b = lds128(cs0 + c * 4), bl = lds128(cs0 + (cst_n + c) * 4), hb = lds128(cs0 + (2 * cst_n + goff + c) * 4);
+    f[k] = gate_one<kElu>(f[k], g[k], b.x, bl.x, hb.x);
+    f[k + 1] = gate_one<kElu>(f[k + 1], g[k + 1], b.y, bl.y, hb.y);
+    f[k + 2] = gate_one<kElu>(f[k + 2], g[k + 2], b.z, bl.z, hb.z);
+    f[k + 3] = gate_one<kElu>(f[k + 3], g[k + 3], b.w, bl.w, hb.w);
+  };
+  auto do16 = [&](int b) {
+    const int c0 = b * 8;
+    float f[16], g[16];
+    tmem_ld16(taddr + c0, f);
+    tmem_ld16(taddr + goff + c0, g);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gate4(f, g, c0 + 4 * q, 4 * q);
+      __nv_bfloat16* o = obase + (size_t)b * ostep;
+      *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      *reinterpret_cast<uint4*>(o + ostep) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+    }
+  };
+  auto do8 = [&](int b) {
+    const int c0 = b * 8;
+    float f[8], g[8];
+    tmem_ld8(taddr + c0, f);
+    tmem_ld8(taddr + goff + c0, g);
+    tmem_ld_wait();
+    if (valid) {
+      gate4(f, g, c0, 0);
+      gate4(f, g, c0 + 4, 4);
+      *reinterpret_cast<uint4*>(obase + (size_t)b * ostep) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+  };
+  if (nsplit == 1) {
+    int b = 0;
+    for (; b + 2 <= nb; b += 2) do16(b);
+    if (b < nb) do8(b);
+  } else if (nb % (2 * nsplit) == 0) {
+    for (int b = 2 * grp; b < nb; b += 2 * nsplit) do16(b);
+  } else {
+    for (int b = grp; b < nb; b += nsplit) do8(b);
+  }
+}
+
 // Drain one accumulator tile (this thread = TMEM lane = one output position) and apply the fused epilogue.
-//   gated : out[c] = act(acc[c] + b[c]) * sigmoid(acc[c + Cout/2] + b[c + Cout/2])   (reference utils.py:29-32)
-//           sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 (one MUFU), ELU's exp as ex2 with the bias folded into the FMA
+//   gated : out[c] = act(acc[c] + b[c]) * sigmoid(acc[goff + c] + b[Cout/2 + c])
 //   linear: out[c] = (acc[c] + b[c]) * scale * colscale[img][c]
 // The 16-column chunks of a tile are dealt round-robin to `nsplit` warp groups (this one is `grp`); nsplit == 1 means
 // this group drains the whole tile (the groups then alternate tiles).
@@ -253,44 +429,25 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& e, const float
         epi_store16<kFast>(e, img, oy, ox, cb, v, cnt);
       }
     }
+  } else if (kFast) {
+    if (e.epi == EPI_GATE_ELU) tc_epilogue_gated_fast<true>(e, cst, cst_n, taddr, img, valid, oy, ox, grp, nsplit);
+    else tc_epilogue_gated_fast<false>(e, cst, cst_n, taddr, img, valid, oy, ox, grp, nsplit);
   } else {
-    const int half = e.Cout >> 1;
+    // general form (fp32 or unaligned NHWC output: single-layer calls through the C ABI)
+    const int half = e.Cout >> 1, goff = e.goff;
     const bool is_elu = (e.epi == EPI_GATE_ELU);
-    const uint32_t cs0 = smem_u32(cst);
     for (int c0 = grp * 16; c0 < half; c0 += 16 * nsplit) {
       float f[16], g[16];
       tmem_ld16(taddr + c0, f);
-      tmem_ld16(taddr + half + c0, g);
+      tmem_ld16(taddr + goff + c0, g);
       tmem_ld_wait();
       if (valid) {
         const int cnt = min(16, half - c0);
-        const bool al = ((half & 3) == 0);   // 16 B aligned constant rows (c0 is a multiple of 16)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float b4[4], bl4[4], hb4[4];
-          if (al) {
-            const float4 b = lds128(cs0 + (c0 + 4 * q) * 4), bl = lds128(cs0 + (cst_n + c0 + 4 * q) * 4);
-            const float4 hb = lds128(cs0 + (2 * cst_n + half + c0 + 4 * q) * 4);
-            b4[0] = b.x; b4[1] = b.y; b4[2] = b.z; b4[3] = b.w;
-            bl4[0] = bl.x; bl4[1] = bl.y; bl4[2] = bl.z; bl4[3] = bl.w;
-            hb4[0] = hb.x; hb4[1] = hb.y; hb4[2] = hb.z; hb4[3] = hb.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              b4[i] = cst[c0 + 4 * q + i];
-              bl4[i] = cst[cst_n + c0 + 4 * q + i];
-              hb4[i] = cst[2 * cst_n + half + c0 + 4 * q + i];
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = 4 * q + i;
-            const float fv = f[k] + b4[i];
-            const float ex = ex2_approx(fmaf(f[k], 1.4426950408889634f, bl4[i])) - 1.0f;
-            const float a = is_elu ? (fv > 0.0f ? fv : ex) : fmaxf(fv, 0.0f);
-            const float sg = fmaf(0.5f, tanh_approx(fmaf(g[k], 0.5f, hb4[i])), 0.5f);     // sigmoid(g + b)
-            f[k] = (k < cnt) ? a * sg : 0.0f;
-          }
+        for (int k = 0; k < 16; ++k) {
+          const float b = cst[c0 + k], bl = cst[cst_n + c0 + k], hb = cst[2 * cst_n + goff + c0 + k];
+          const float o = is_elu ? gate_one<true>(f[k], g[k], b, bl, hb) : gate_one<false>(f[k], g[k], b, bl, hb);
+          f[k] = (k < cnt) ? o : 0.0f;
         }
         epi_store16<kFast>(e, img, oy, ox, c0, f, cnt);
       }
