@@ -67,6 +67,7 @@ struct ConvParams {
   int Ho, Wo, stride;
   int ntaps;
   int8_t dy[MAX_TAPS], dx[MAX_TAPS];
+  int8_t tap_cb[MAX_TAPS];   // C8 input only: first channel block read by tap t (space-to-depth layers), else 0
   // weights / bias
   const void* w;        // layout depends on the kernel (see se_conv_direct.cu / se_conv_tc.cu)
   long long w_img_stride;   // elements between images (0 = shared)
@@ -88,7 +89,7 @@ struct ConvParams {
 // choff) or C8 = [N][CBtot][H][W][8] (ldo = CBtot channel blocks, choff multiple of 8).
 struct EpiParams {
   void* y;
-  int out_dt, out_c8;
+  int out_dt, out_c8;   // out_c8: 0 NHWC, 1 channel-blocked, 2 channel-blocked space-to-depth (see epilogue)
   int Hout, Wout, ldo, choff;
   int osy, ooy, osx, oox;
   int epi;

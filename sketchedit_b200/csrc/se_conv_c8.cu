@@ -365,8 +365,13 @@ static const int kSmemBudget = 200 * 1024;
 static const int kResidentMax = 112 * 1024;
 
 // geometry shared by the weight packer (stage grouping) and the launcher
-int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem) {
+int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem, const int8_t* tap_cb) {
   L->stem = stem;
+  int cb_max = 0;
+  for (int t = 0; t < ntaps; ++t) {
+    L->tap_cb[t] = tap_cb ? tap_cb[t] : 0;
+    cb_max = L->tap_cb[t] > cb_max ? L->tap_cb[t] : cb_max;
+  }
   int mn_y = 0, mx_y = 0, mn_x = 0, mx_x = 0;
   for (int t = 0; t < ntaps; ++t) {
     mn_y = dy[t] < mn_y ? dy[t] : mn_y; mx_y = dy[t] > mx_y ? dy[t] : mx_y;
@@ -385,7 +390,9 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
   }
   // the box covers the zero-padded GEMM K (whole 64 / 32 channel chunks): blocks past the tensor are TMA zero fill,
   // so the MMAs never multiply stale shared memory (possibly NaN bit patterns) by the zero weight columns
-  L->cb_in = stem ? 1 : (w.n64 * 64 + w.n32 * 32) / 8;
+  // (space-to-depth layers: a tap starts at its own channel block; the zero weight columns of its last chunk may then
+  //  multiply the next parity's finite activations instead of TMA zeros, which is just as harmless)
+  L->cb_in = stem ? 1 : cb_max + (w.n64 * 64 + w.n32 * 32) / 8;
   const long long halo_bytes = (long long)L->cb_in * HR * WR * 16;
   w.NT = (gated_goff(Cout) + Cout / 2 + 15) / 16 * 16;   // every layer on this path is gated: gate columns start at goff
   w.n_tiles = 1;
@@ -484,6 +491,7 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   SE_REQUIRE(c.stride == 1, "conv_c8 handles stride-1 convolutions");
   SE_REQUIRE((reinterpret_cast<uintptr_t>(c.x) & 127) == 0, "input base must be 128 B aligned");
   SE_REQUIRE(c.ntaps == w.ntaps && c.ntaps <= MAX_TAPS, "tap count mismatch");
+  for (int t = 0; t < c.ntaps; ++t) SE_REQUIRE(c.tap_cb[t] == L.tap_cb[t] && (L.tap_cb[t] == 0 || L.mode == C8_HALO), "per-tap channel blocks need the halo mode");
   SE_REQUIRE(c.Wi * 8 <= (1 << 30) && L.WR * 8 <= 256 && L.HR <= 256 && L.cb_in <= 256, "TMA box limits");
   C8Params p;
   memset(&p, 0, sizeof(p));
@@ -515,13 +523,15 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
     for (int u = 0; u < n_u64 + n_u32; ++u) {
       const bool is64 = u < n_u64;
       const int t = is64 ? u / w.n64 : u - n_u64;
-      const int cb0 = is64 ? (u - t * w.n64) * 8 : w.n64 * 8;
+      const int cb0 = L.tap_cb[t] + (is64 ? (u - t * w.n64) * 8 : w.n64 * 8);
       const int oy = halo ? c.dy[t] + L.pad_y0 : 0, ox = halo ? c.dx[t] + L.pad_x0 : 0;
       p.aoff[u] = (uint32_t)((cb0 * L.HR + oy) * L.WR + ox) * 16u;
     }
   }
   SE_REQUIRE(c.epi == EPI_LINEAR || (c.Cout % 2 == 0 && c.out_dt == DT_BF16), "gated epilogue needs even Cout, bf16 out");
   SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
+  SE_REQUIRE(c.out_c8 != 2 || (c.epi != EPI_LINEAR && c.Hout % 2 == 0 && c.Wout % 2 == 0 && c.ldo % 4 == 0 && (c.Cout / 2) % 8 == 0),
+             "space-to-depth output: gated layer, even size, whole channel blocks");
 
   const int total_tiles = p.N * p.tiles_x * p.tiles_y;
   const bool pair = L.w_pair != nullptr && total_tiles % 2 == 0;

@@ -19,6 +19,7 @@ struct C8Layer {
   int HR = 0, WR = 0;   // rows / columns of the shared-memory A region
   int pad_y0 = 0, pad_x0 = 0;
   int a_bytes = 0, a_tx_bytes = 0;
+  int8_t tap_cb[MAX_TAPS] = {0};   // first channel block read by each tap (0 except space-to-depth layers)
   const void* w_pair = nullptr;   // CTA-pair format of the stage images (each stage = [rows 0..NT/2) | rows NT/2..NT)), or null
 };
 
@@ -40,7 +41,7 @@ struct C8Params {
   unsigned long long* dbg;
 };
 
-int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem);
+int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem, const int8_t* tap_cb = nullptr);
 bool c8_pair_capable(const C8Layer& L);
 // byte offset of element (unit, n, k) of a stage in the CTA-pair image: the two row halves are separate sub-images
 inline uint32_t c8_pair_image_offset(const TcWeights& w, bool is64, int j, int n, int k) {

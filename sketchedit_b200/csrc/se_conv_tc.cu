@@ -319,6 +319,7 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   p.bias = c.bias;
   fill_epi(c, w.NT, &p.e);
   SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
+  SE_REQUIRE(c.out_c8 != 2, "space-to-depth output is written by the channel-blocked kernel only");
   if (c.epi != EPI_LINEAR) {
     SE_REQUIRE(w.n_tiles == 1 && c.Cout % 2 == 0 && c.out_dt == DT_BF16, "gated epilogue needs one N tile, even Cout, bf16 out");
   }

@@ -124,6 +124,11 @@ struct ClassW {
   bool has_tc = false;
   C8Layer c8;                  // se_conv_c8.cu: channel-blocked input (every stride-1 layer on the bf16 path)
   bool use_c8 = false;
+  // stride-2 3x3 layers on the tensor-core path read a SPACE-TO-DEPTH channel-blocked input (written that way by
+  // the producing layer's epilogue): tap (ky,kx) of output (y,x) reads input row 2y+ky-1 = row y+c8dy of parity
+  // (ky-1)&1, i.e. a stride-1 read at offset (c8dy, c8dx) starting at channel block c8cb = parity * Ci/8
+  bool s2d = false;
+  int8_t c8dy[MAX_TAPS], c8dx[MAX_TAPS], c8cb[MAX_TAPS];
   int osy = 1, ooy = 0, osx = 1, oox = 0;
 };
 
@@ -206,10 +211,23 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
   }
   cw.has_tc = (Ci % 8 == 0) && !L.is_head;
   if (cw.has_tc) {
-    cw.use_c8 = (s.stride == 1);
+    cw.s2d = (s.stride == 2 && s.k == 3 && s.rate == 1 && !s.deconv && !L.is_stem && Ci % 8 == 0);
+    cw.use_c8 = (s.stride == 1) || cw.s2d;
+    memset(cw.c8cb, 0, sizeof(cw.c8cb));
+    memcpy(cw.c8dy, cw.dy, sizeof(cw.c8dy));
+    memcpy(cw.c8dx, cw.dx, sizeof(cw.c8dx));
+    if (cw.s2d) {
+      for (int t = 0; t < cw.ntaps; ++t) {
+        const int oy = cw.dy[t], ox = cw.dx[t];          // -1, 0, +1 (input row 2y + oy)
+        const int py = oy & 1, px = ox & 1;              // parity of that row / column
+        cw.c8dy[t] = (int8_t)((oy - py) / 2);            // -1 for oy = -1, else 0
+        cw.c8dx[t] = (int8_t)((ox - px) / 2);
+        cw.c8cb[t] = (int8_t)((py * 2 + px) * (Ci / 8));
+      }
+    }
     TcWeights* tcp;
     if (cw.use_c8) {
-      int rc = c8_configure(&cw.c8, cw.ntaps, cw.dy, cw.dx, Ci, Cout, L.is_stem);
+      int rc = c8_configure(&cw.c8, cw.ntaps, cw.c8dy, cw.c8dx, Ci, Cout, L.is_stem, cw.c8cb);
       if (rc) return rc;
       tcp = &cw.c8.w;
     } else {
@@ -465,7 +483,12 @@ static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw, double fl
 
 // one gated conv / deconv layer: in (Hi x Wi x Ci) -> out view (channels written at [choff, choff+cout_g))
 // layout a layer wants for its input on the bf16 tensor-core path (stride-2 layers read NHWC, the rest C8)
-static int wants_c8(const Ctx& c, const Layer& L) { return (c.prec == SE_PREC_BF16_TC && !L.is_head && L.spec.stride == 1) ? 1 : 0; }
+// 0 NHWC, 1 channel-blocked (C8), 2 channel-blocked space-to-depth (stride-2 layers)
+static int wants_c8(const Ctx& c, const Layer& L) {
+  if (c.prec != SE_PREC_BF16_TC || L.is_head) return 0;
+  if (L.spec.stride == 1) return 1;
+  return (!L.cls.empty() && L.cls[0].s2d) ? 2 : 0;
+}
 static inline size_t act_bytes(const Ctx& c, int H, int W, int C, int c8) {
   return c8 ? (size_t)c.B * ((C + 7) / 8) * H * W * 16 : (size_t)c.B * H * W * C * c.esz();
 }
@@ -501,6 +524,13 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     cp.ntaps = cw.ntaps;
     memcpy(cp.dy, cw.dy, sizeof(cp.dy));
     memcpy(cp.dx, cw.dx, sizeof(cp.dx));
+    if (in.c8 == 2) {   // space-to-depth input: a stride-1 problem on the half-resolution grid with per-tap parity blocks
+      SE_REQUIRE(cw.s2d && in.H % 2 == 0 && in.W % 2 == 0, "space-to-depth input at layer " + L.name);
+      cp.Hi = in.H / 2; cp.Wi = in.W / 2; cp.stride = 1;
+      memcpy(cp.dy, cw.c8dy, sizeof(cp.dy));
+      memcpy(cp.dx, cw.c8dx, sizeof(cp.dx));
+      memcpy(cp.tap_cb, cw.c8cb, sizeof(cp.tap_cb));
+    }
     cp.w = nullptr; cp.w_img_stride = 0;
     cp.bias = L.bias; cp.Cout = s.cout;
     cp.y = out; cp.out_dt = c.act_dt();
@@ -515,7 +545,7 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
   if (dbg && !c.dry && c.act_dt() == DT_BF16) {
     const int cg = s.cout / 2, Hout = Ho * L.cls[0].osy, Wout = Wo * L.cls[0].osx;
     const long long n_out = out_c8 ? (long long)c.B * ldo * Hout * Wout * 8 : (long long)c.B * Hout * Wout * ldo;
-    const long long n_in = in.c8 ? (long long)c.B * in.ld * in.H * (L.is_stem ? stem_wp(in.W) : in.W) * 8 : (long long)c.B * in.H * in.W * in.ld;
+    const long long n_in = in.c8 ? (long long)c.B * in.ld * in.H * (L.is_stem ? stem_wp(in.W) : in.W) * 8 / (in.c8 == 2 ? 4 : 1) : (long long)c.B * in.H * in.W * in.ld;
     fprintf(stderr, "[nan] %-28s in %dx%d c8=%d ld=%d nonfinite_in=%lld | out %dx%d c8=%d ld=%d choff=%d cg=%d nonfinite_out(buffer)=%lld use_c8=%d mode=%d res=%d\n", L.name.c_str(), in.H, in.W,
             in.c8, in.ld, count_nonfinite_bf16(in.p, n_in, c.stream), Hout, Wout, out_c8, ldo, choff, cg, count_nonfinite_bf16(out, n_out, c.stream), (int)L.cls[0].use_c8,
             L.cls[0].c8.mode, (int)L.cls[0].c8.resident);
@@ -559,7 +589,8 @@ static int run_chain(Ctx& c, char net, const std::vector<std::string>& names, Vi
       }
       nb = c.get(act_bytes(c, Ho, Wo, cg, oc8));
       nxt = oc8 ? c8view(nb.p, Ho, Wo, cg, (cg + 7) / 8, 0) : nhwc(nb.p, Ho, Wo, cg, cg);
-      int rc = run_layer(c, *L, cur, nb.p, oc8 ? (cg + 7) / 8 : cg, 0, oc8);
+      if (oc8 == 2) { nxt.c8 = 2; nxt.ld = 4 * (cg / 8); }   // [N][4*cg/8][Ho/2][Wo/2][8]
+      int rc = run_layer(c, *L, cur, nb.p, oc8 ? nxt.ld : cg, 0, oc8);
       if (rc) return rc;
     }
     if (cur_owned) c.put(cur_buf);
@@ -990,6 +1021,8 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
     if (L->is_stem) {
       CK(fill_zero(in.p, in.bytes, st));
       CK(nchw_to_stem8(x, in.p, dt, B, s.cin, H, W, stem_wp(W), STEM_PADL, st));
+    } else if (in_c8 == 2) {
+      CK(nchw_to_c8_s2d(x, in.p, B, s.cin, H, W, st));
     } else if (in_c8) {
       if (s.cin % 8) CK(fill_zero(in.p, in.bytes, st));
       CK(nchw_to_c8(x, in.p, B, s.cin, H * W, st));
@@ -1018,6 +1051,7 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
       const int cg = s.cout / 2;
       Buf o = c.get((size_t)B * Ho * Wo * cg * c.esz());
       View vin = L->is_stem ? stem_view(c, in.p, H, W) : (in_c8 ? c8view(in.p, H, W, Ci, (Ci + 7) / 8, 0) : nhwc(in.p, H, W, Ci, Ci));
+      if (in_c8 == 2) { vin.c8 = 2; vin.ld = 4 * (Ci / 8); }
       int r = run_layer(c, *L, vin, o.p, cg, 0, 0);
       if (r) return r;
       CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, st));

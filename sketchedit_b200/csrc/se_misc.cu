@@ -637,6 +637,29 @@ int nchw_to_c8(const float* x, void* y, int B, int C, int HW, cudaStream_t s) {
   return 0;
 }
 
+// NCHW fp32 -> space-to-depth C8 bf16 [B][4*C/8][H/2][W/2][8]: pixel (y, x) channel c lands in channel block
+// ((y&1)*2 + (x&1)) * C/8 + c/8 at position (y/2, x/2)  (C % 8 == 0, H and W even)
+__global__ void nchw_to_c8_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int H, int W, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int px = (int)(i % W);
+  long long r = i / W;
+  const int py = (int)(r % H);
+  r /= H;
+  const int c = (int)(r % C);
+  const long long b = r / C;
+  const int CB = C / 8, Hs = H / 2, Ws = W / 2;
+  const int blk = ((py & 1) * 2 + (px & 1)) * CB + (c >> 3);
+  y[(((b * 4 * CB + blk) * Hs + (py >> 1)) * Ws + (px >> 1)) * 8 + (c & 7)] = __float2bfloat16(x[i]);
+}
+int nchw_to_c8_s2d(const float* x, void* y, int B, int C, int H, int W, cudaStream_t s) {
+  SE_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "space-to-depth C8 needs C % 8 == 0 and even H, W");
+  const long long total = (long long)B * C * H * W;
+  nchw_to_c8_s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, (__nv_bfloat16*)y, C, H, W, total);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s) {
   const long long total = (long long)B * C * HW;
   SE_DISPATCH_T(dt, (nchw_to_nhwc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, (T*)y, C, HW, ldo, choff, total)));

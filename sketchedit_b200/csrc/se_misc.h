@@ -23,6 +23,7 @@ int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, in
                long long pc_bytes, cudaStream_t s);
 int softmax_rows(const float* S, int lds, void* P, int dt, int ldp, long long rows, int L, cudaStream_t s);
 int nchw_to_stem8(const float* x, void* y, int dt, int B, int cin, int H, int W, int Wp, int padl, cudaStream_t s);
+int nchw_to_c8_s2d(const float* x, void* y, int B, int C, int H, int W, cudaStream_t s);
 int nchw_to_c8(const float* x, void* y, int B, int C, int HW, cudaStream_t s);
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s);
 int nhwc_to_nchw(const void* x, int dt, float* y, int B, int C, int HW, int ldx, int choff, cudaStream_t s);

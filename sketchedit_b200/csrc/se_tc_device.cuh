@@ -348,7 +348,13 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
   const uint32_t cs0 = smem_u32(cst);
   __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(e.y);
   size_t ostep;   // elements between consecutive 8-channel blocks of this pixel
-  if (e.out_c8) {
+  if (e.out_c8 == 2) {
+    // space-to-depth for a stride-2 consumer: [N][4 * ldo/4 blocks][Hout/2][Wout/2][8], parity (oy&1, ox&1) selects
+    // the block group, so the consumer's taps become plain stride-1 reads of one parity each
+    const int Hs = e.Hout >> 1, Ws = e.Wout >> 1, par = ((oy & 1) << 1) | (ox & 1);
+    ostep = (size_t)Hs * Ws * 8;
+    obase += (((size_t)img * e.ldo + par * (e.ldo >> 2) + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws * 8 + (size_t)(ox >> 1) * 8;
+  } else if (e.out_c8) {
     ostep = (size_t)e.Hout * e.Wout * 8;
     obase += (((size_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout * 8 + (size_t)ox * 8;
   } else {
