@@ -92,14 +92,20 @@ class Engine:
         return e
 
     # -------------------------------------------------------------------------------- forward
-    def inference(self, image, sketch, precision="bf16", want=(), mask_bin=None):
+    def inference(self, image, sketch, precision="bf16", want=(), mask_bin=None, out=None):
         """EditLine2Model.forward(mode='inference'): returns (composed, mask) and, in a dict, any of
-        want = ('coarse', 'fine', 'mask_image', 'mask_bin')."""
+        want = ('coarse', 'fine', 'mask_image', 'mask_bin'). ``out=(composed, mask)`` writes into caller-owned
+        fp32 CUDA tensors of shape [B,3,H,W] / [B,1,H,W] instead of allocating (pipelined callers)."""
         image = _chk_in(image, name="image")
         sketch = _chk_in(sketch, name="sketch")
         B, _, H, W = image.shape
         new = lambda c: torch.empty(B, c, H, W, device=image.device, dtype=torch.float32)
-        composed, mask = new(3), new(1)
+        if out is not None:
+            composed, mask = _chk_in(out[0], name="out[0]"), _chk_in(out[1], name="out[1]")
+            if tuple(composed.shape) != (B, 3, H, W) or tuple(mask.shape) != (B, 1, H, W):
+                raise _lib.SketchEditB200Error("out tensors must be [B,3,H,W] and [B,1,H,W]")
+        else:
+            composed, mask = new(3), new(1)
         extra = {k: new(1 if k == "mask_bin" else 3) for k in want}
         mb_in = _chk_in(mask_bin, name="mask_bin") if mask_bin is not None else None
         _lib.check(self.lib.se_forward_inference(

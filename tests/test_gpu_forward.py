@@ -115,3 +115,28 @@ def test_uint8_outputs():
     g, m = O.to_uint8_outputs(composed.cpu(), mask.cpu())
     assert np.array_equal(bgr.cpu().numpy(), g.transpose(0, 2, 3, 1)[..., ::-1])
     assert np.array_equal(mk.cpu().numpy(), m)
+
+
+def test_inference_stream_matches_blocking_calls():
+    """models.EditLine2Model.inference_stream (copies on side streams, double-buffered) returns, in order and bit for
+    bit, what one blocking model(data, mode='inference') call per batch returns - including a ragged last batch."""
+    from argparse import Namespace
+
+    import models
+    opt = Namespace(gpu_ids=[0], isTrain=False, isSkip=True, netG="deepfillc2", init_type="xavier", init_variance=0.02,
+                    use_cam=True, pool_type="max", no_mask_cc=False, no_mask_coarse=False, joint_train_inp=True,
+                    model="editline2", precision="bf16")
+    model = models.create_model(opt)
+    model.netM.load_state_dict(synth.synth_state_dict("M"))
+    model.netG.load_state_dict(synth.synth_state_dict("G"))
+    model.eval()
+    batches = []
+    for i, b in enumerate((2, 2, 2, 2, 1)):
+        img, sk = synth.synth_inputs(b, 64, 64, seed=20 + i)
+        batches.append({"image": img.pin_memory(), "mask": sk.pin_memory()})
+    with torch.no_grad():
+        want = [tuple(t.cpu() for t in model(d, mode="inference")) for d in batches]
+        got = list(model.inference_stream(iter(batches)))
+    assert len(got) == len(want)
+    for (gc, gm), (wc, wm) in zip(got, want):
+        assert gc.is_pinned() and torch.equal(gc, wc) and torch.equal(gm, wm)
