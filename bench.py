@@ -45,7 +45,7 @@ def make_inputs(batch):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 25 ms during the timed regions (device-resident + e2e)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -234,7 +234,6 @@ def run_b200(args):
         _lib.check(lib.se_tc_time_ms(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         tc_ms, tc_n, tc_fl = a.value, b.value, c.value
         lib.se_tc_timing_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -277,6 +276,7 @@ def run_b200(args):
 
     run_stream(3)
     e2e_value = world * B * args.steps / timed(lambda: run_stream(args.steps))
+    clocks = sampler.stop() if rank == 0 else None
     h2d = B * 4 * H * W * 4
     d2h = B * 4 * H * W * 4
 

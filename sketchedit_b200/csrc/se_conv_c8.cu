@@ -206,7 +206,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
     int stage = 0, iter = 0;
     uint32_t phase = 0;
-    long long t_wfull = 0, t_wtmem = 0, t_begin = clock64();
+    long long t_wfull = 0, t_wtmem = 0, t_whalo = 0, t_begin = clock64();
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t off_wres = halo ? (uint32_t)(p.a_bufs * p.a_bytes) : 0u;
     const uint32_t off_stages = off_wres + (p.resident ? (uint32_t)p.wres_bytes : 0u);
@@ -222,7 +222,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (halo) {
         tw = p.dbg ? clock64() : 0;
         mbar_wait(&a_full[ab], (iter >> p.a_shift) & 1, 7);
-        if (p.dbg) t_wfull += clock64() - tw;
+        if (p.dbg) t_whalo += clock64() - tw;
       }
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * acc_stride;
@@ -294,7 +294,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (staged && ++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
-    if (p.dbg && lane == 0 && warp == 1) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; }
+    if (p.dbg && lane == 0 && warp == 1) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 7] = t_whalo; }
   } else if (warp >= 4) {
     // ==================================================================== epilogue
     const int q = warp & 3;
@@ -427,9 +427,10 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
 }
 
 // the k-step structures of the generator's layers get their own fully unrolled instantiation
-#define C8_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(1, 0, 4) X(1, 1, 4) X(4, 4, 4) X(4, 0, 4) X(0, 3, 4) X(0, 1, 4)
-// k-step structures of the streamed-weight layers that run as CTA pairs (96->192: <1,1>; 192/48/384->192: <1,0>)
-#define C8_PAIR_SPECIALISATIONS(X) X(1, 0, 4) X(1, 1, 4)
+#define C8_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(1, 0, 4) X(1, 1, 4) X(4, 4, 4) X(4, 0, 4) X(0, 3, 4) X(0, 1, 4) X(3, 0, 4)
+// k-step structures of the streamed-weight layers that run as CTA pairs (96->192: <1,1>; 192/48->192: <1,0>;
+// the 48->96 stride-2 layer of the refine branch: <3,0>)
+#define C8_PAIR_SPECIALISATIONS(X) X(1, 0, 4) X(1, 1, 4) X(3, 0, 4)
 static int c8_set_smem_attr(int bytes) {
 #define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   C8_SPECIALISATIONS(X)
@@ -613,9 +614,9 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
     for (int b = 0; b < grid; ++b)
       for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 8 + k] / grid;
     fprintf(stderr,
-            "[c8] N=%d %dx%d Ci=%d taps=%d NT=%d mode=%s pair=%d res=%d HRxWR=%dx%d abufs=%d n64=%d n32=%d r64=%d r32=%d stages=%d tiles=%d | prod wait %.0f/%.0f | mma wait_full %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f\n",
+            "[c8] N=%d %dx%d Ci=%d taps=%d NT=%d mode=%s pair=%d res=%d HRxWR=%dx%d abufs=%d n64=%d n32=%d r64=%d r32=%d stages=%d tiles=%d | prod wait %.0f/%.0f | mma wait_full %.0f wait_halo %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f\n",
             c.N, c.Ho, c.Wo, c.Ci, c.ntaps, p.NT, L.mode == C8_HALO ? "halo" : "pertap", (int)pair, p.resident, L.HR, L.WR, p.a_bufs, p.n64, p.n32, p.r64, p.r32,
-            p.num_stages, total_tiles, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+            p.num_stages, total_tiles, a[0], a[1], a[2], a[7], a[3], a[4], a[5], a[6]);
   }
   return 0;
 }

@@ -143,6 +143,7 @@ struct Layer {
   std::vector<ClassW> cls;
   float* bias = nullptr;       // device [cout]
   float* w_head = nullptr;     // device [9][12][cout] (heads)
+  std::vector<float> w_head_host;   // same, host copy (kernel-parameter weights of the channel-blocked head kernel)
 };
 
 }  // namespace se
@@ -304,6 +305,7 @@ static int pack_layer(se_model* m, Layer& L) {
         for (int o = 0; o < s.cout; ++o) wh[((size_t)t * 12 + c) * s.cout + o] = L.w_host[(((size_t)o * 12 + c) * 3 + t / 3) * 3 + t % 3];
     rc = upload(m, wh.data(), wh.size() * 4, (void**)&L.w_head);
     if (rc) return rc;
+    L.w_head_host = wh;
   }
   if (L.is_stem) {
     // 5x5 / pad 2 over <= 5 real channels: K per tap would be 3-5. Instead one 64-wide GEMM-K chunk covers a
@@ -613,6 +615,11 @@ static int run_head(Ctx& c, char net, const std::string& name, const View& in, i
                     const float* mask_soft, float* out_nchw, float* out2, void* out_pack8) {
   Layer* L = find_ready(c.m, net, name);
   SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name + ": " + last_error());
+  if (in.c8 == 1 && c.act_dt() == DT_BF16) {
+    CK(head_c8(in.p, L->w_head_host.data(), L->b_host.data(), L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
+               out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, c.stream));
+    return 0;
+  }
   CK(head(in.p, c.act_dt(), in.c8, L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
           out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, c.stream));
   return 0;

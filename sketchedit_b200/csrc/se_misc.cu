@@ -147,6 +147,117 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
   }
 }
 
+// bf16 channel-blocked input (the tensor-core path): same arithmetic, organised for the FP32 pipe.
+//   * weights come in as a by-value kernel parameter: they sit in the constant bank and feed the FMAs directly
+//     (the generic kernel spends one shared-memory load per FMA)
+//   * channels are processed in pairs with the packed fma.rn.f32x2 (two FMAs per issue slot): a bf16x2 word expands
+//     to the (even, odd) channel pair, the weights are stored as matching pairs, and each output keeps an (even, odd)
+//     pair of partial sums that is added at the end
+template <int COUT>
+struct HeadWeights {
+  float2 w[9][6][COUT];   // [tap][channel pair][out] = (w[tap][2p][o], w[tap][2p+1][o])
+  float b[COUT];
+};
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+template <int COUT>
+__global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __restrict__ x, const __grid_constant__ HeadWeights<COUT> hw, int B, int H,
+                                                      int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
+                                                      const float* __restrict__ mask_soft, float* __restrict__ out_nchw,
+                                                      float* __restrict__ out2, __nv_bfloat16* __restrict__ out_pack8, int no_mask_coarse,
+                                                      int Wp, int padl) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W;
+  if (i >= B * HW) return;
+  const long long b = i / HW, pix = i % HW;
+  const int yy = (int)(pix / W), xx = (int)(pix % W);
+  unsigned long long acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0ull;
+  const uint4* plane0 = reinterpret_cast<const uint4*>(x) + (b * 2) * HW;   // [b][2 blocks][H][W] x 16 B
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const uint4 q0 = plane0[(long long)iy * W + ix];
+    const uint4 q1 = plane0[HW + (long long)iy * W + ix];             // channels 8..15 (12..15 are padding)
+    const uint32_t wds[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      // bf16x2 -> (even channel, odd channel) as an fp32 pair
+      const unsigned long long xp = ((unsigned long long)(wds[p] & 0xffff0000u) << 32) | (unsigned long long)(wds[p] << 16);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float2 wv = hw.w[t][p][o];
+        const unsigned long long wp = ((unsigned long long)__float_as_uint(wv.y) << 32) | __float_as_uint(wv.x);
+        acc[o] = ffma2(xp, wp, acc[o]);
+      }
+    }
+  }
+  float r[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) r[o] = hw.b[o] + (__uint_as_float((uint32_t)acc[o]) + __uint_as_float((uint32_t)(acc[o] >> 32)));
+  if (mode == HEAD_MASK) {
+    const float sg = 1.0f / (1.0f + expf(-r[0]));
+    out_nchw[i] = sg;
+    out2[i] = sg > 0.5f ? 1.0f : 0.0f;
+    return;
+  }
+  float t3[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) t3[o] = tanhf(r[o]);
+  if (mode == HEAD_TANH) {
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+  } else if (mode == HEAD_COARSE) {
+    const float m = mask_bin[i];
+    __align__(16) __nv_bfloat16 pk[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) pk[o] = __float2bfloat16(0.0f);
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      if (out_nchw) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+      const float xin = img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      pk[o] = __float2bfloat16(no_mask_coarse ? t3[o] : (t3[o] * m + xin * (1.0f - m)));
+    }
+    *reinterpret_cast<uint4*>(out_pack8 + ((b * H + yy) * Wp + xx + padl) * 8) = *reinterpret_cast<const uint4*>(pk);
+  } else {  // HEAD_FINE
+    const float m = mask_soft[i];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      if (out2) out2[(b * COUT + o) * HW + pix] = t3[o];
+      out_nchw[(b * COUT + o) * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+    }
+  }
+}
+
+template <int COUT>
+static int head_c8_launch(const void* x, const float* w_host, const float* b_host, int B, int H, int W, int mode, const float* img,
+                          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
+                          int Wp, int padl, cudaStream_t s) {
+  HeadWeights<COUT> hw;
+  for (int t = 0; t < 9; ++t)
+    for (int p = 0; p < 6; ++p)
+      for (int o = 0; o < COUT; ++o) hw.w[t][p][o] = make_float2(w_host[(t * 12 + 2 * p) * COUT + o], w_host[(t * 12 + 2 * p + 1) * COUT + o]);
+  for (int o = 0; o < COUT; ++o) hw.b[o] = b_host[o];
+  const long long n = (long long)B * H * W;
+  head_c8_kernel<COUT><<<cdiv(n, 128), 128, 0, s>>>((const __nv_bfloat16*)x, hw, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2,
+                                                    (__nv_bfloat16*)out_pack8, no_mask_coarse, Wp, padl);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// w_host / b_host: host copies of the [9][12][cout] weights and the bias (kernel parameters are built from them)
+int head_c8(const void* x, const float* w_host, const float* b_host, int cout, int B, int H, int W, int mode, const float* img,
+            const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse, int Wp, int padl,
+            cudaStream_t s) {
+  SE_REQUIRE(cout == 1 || cout == 3, "head cout");
+  if (cout == 1) return head_c8_launch<1>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, s);
+  return head_c8_launch<3>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, s);
+}
+
 int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
          int Wp, int padl, cudaStream_t s) {

@@ -401,6 +401,26 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     if (b < nb) do8(b);
   } else if (nb % (2 * nsplit) == 0) {
     for (int b = 2 * grp; b < nb; b += 2 * nsplit) do16(b);
+  } else if (nb == 3 * nsplit) {
+    // three 8-column blocks per group (192-column tiles over 4 groups): all six TMEM loads are issued before the
+    // single wait, so their latency (long while the MMAs of the next tile stream accumulators) is paid once, not 3x
+    float f[3][8], g[3][8];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      tmem_ld8(taddr + (grp + j * nsplit) * 8, f[j]);
+      tmem_ld8(taddr + goff + (grp + j * nsplit) * 8, g[j]);
+    }
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int bb = grp + j * nsplit;
+        gate4(f[j], g[j], bb * 8, 0);
+        gate4(f[j], g[j], bb * 8 + 4, 4);
+        *reinterpret_cast<uint4*>(obase + (size_t)bb * ostep) =
+            make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]), pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
+      }
+    }
   } else {
     for (int b = grp; b < nb; b += nsplit) do8(b);
   }

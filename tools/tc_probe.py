@@ -7,7 +7,7 @@ from sketchedit_b200.arch import layer_map
 B = int(os.environ.get("PB", "32"))
 cases = [("M", "conv5", 64, 64), ("G", "conv11", 64, 64), ("M", "conv3", 128, 128), ("M", "conv1", 256, 256),
          ("M", "conv13_upsample_conv", 64, 64), ("M", "conv15_upsample_conv", 128, 128), ("M", "conv16", 256, 256),
-         ("M", "conv2_downsample", 256, 256), ("M", "conv4_downsample", 128, 128), ("M", "conv10_atrous", 64, 64)]
+         ("M", "conv2_downsample", 256, 256), ("M", "conv4_downsample", 128, 128), ("G", "xconv4_downsample", 128, 128), ("M", "conv10_atrous", 64, 64)]
 sel = os.environ.get("SE_PROBE_CASES")
 if sel:
     cases = [c for c in cases if c[1] in sel.split(",")]
