@@ -75,13 +75,18 @@ class EditLine2Model(torch.nn.Module):
                     "composed": ex["fine"] * mb + image * (1 - mb), "gt": data.get("gt", data["image"])}
         raise ValueError("|mode| is invalid or training-only: %r" % (mode,))
 
-    def inference_stream(self, loader, depth=2):
+    def inference_stream(self, loader, depth=2, pinned_ring=True):
         """Pipelined form of ``for data in loader: model(data, mode='inference')`` for throughput serving.
 
         Yields ``(composed, mask)`` per batch, in order, as PINNED CPU tensors. The host->device copy of batch
         i+1 and the device->host copy of batch i-1 run on their own CUDA streams while batch i computes
         (``depth`` device buffers per tensor), so a step costs max(copy, compute) instead of their sum.
-        Batches whose 'image'/'mask' tensors are in pinned memory (DataLoader(pin_memory=True)) overlap fully."""
+        Batches whose 'image'/'mask' tensors are in pinned memory (DataLoader(pin_memory=True)) overlap fully.
+
+        pinned_ring=True (default): results are views of a ring of ``depth + 2`` pinned buffers, valid until
+        ``depth + 1`` further results have been drawn (consume or ``.clone()`` them, as a save-to-disk loop does);
+        pinned_ring=False allocates fresh pinned tensors for every batch (a cudaHostAlloc per batch when the host
+        allocator cannot recycle, which costs more than the copy itself)."""
         import collections
         eng = self.engine()
         dev = torch.device("cuda")
@@ -89,6 +94,17 @@ class EditLine2Model(torch.nn.Module):
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         slots = [None] * depth
         pending = collections.deque()
+        ring, ring_pos = {}, [0]
+
+        def host_out(B, H, W):
+            if not pinned_ring:
+                return torch.empty(B, 3, H, W, pin_memory=True), torch.empty(B, 1, H, W, pin_memory=True)
+            bufs = ring.setdefault((B, H, W), [])
+            if len(bufs) < depth + 2:
+                bufs.append((torch.empty(B, 3, H, W, pin_memory=True), torch.empty(B, 1, H, W, pin_memory=True)))
+                return bufs[-1]
+            ring_pos[0] += 1
+            return bufs[ring_pos[0] % (depth + 2)]
 
         def drain_one():
             comp_h, mask_h, ev = pending.popleft()
@@ -118,8 +134,7 @@ class EditLine2Model(torch.nn.Module):
             slot["ev_comp"].record(cur)
             s_out.wait_event(slot["ev_comp"])
             with torch.cuda.stream(s_out):
-                comp_h = torch.empty(B, 3, H, W, pin_memory=True)
-                mask_h = torch.empty(B, 1, H, W, pin_memory=True)
+                comp_h, mask_h = host_out(B, H, W)
                 comp_h.copy_(slot["comp"], non_blocking=True)
                 mask_h.copy_(slot["mask"], non_blocking=True)
                 slot["ev_out"].record(s_out)

@@ -179,7 +179,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (kPair) {
               const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
               if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
-              tma_load_2d_pair(st + stage_a, &tmB, lead_bar, 0, (ks * 2 + (int)cta_rank) * (b_bytes >> 7));
+              tma_load_2d_pair(st + stage_a, &tmB, lead_bar, 0, (ks * 2 + (int)cta_rank) * (b_bytes >> 9));   // 512 B rows
               if (!halo) tma_load_4d_pair(st, &tmA, lead_bar, (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off, img);
             } else {
               mbar_expect_tx(&full_bar[stage], (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
@@ -482,8 +482,8 @@ bool c8_pair_capable(const C8Layer& L) {
   static const bool off = getenv("SE_C8_NOPAIR") != nullptr;
   const TcWeights& w = L.w;
   if (off || L.resident || L.stem || w.NT % 32 != 0) return false;
-  const int rows_half = (w.NT / 2) * (w.r64 * 128 + w.r32 * 64) / 128;
-  return rows_half <= 256 && c8_pair_kernel_exists(w.n64 ? w.r64 : 0, w.n32 ? w.r32 : 0, 4);
+  const int half_bytes = (w.NT / 2) * (w.r64 * 128 + w.r32 * 64);
+  return half_bytes % 512 == 0 && c8_pair_kernel_exists(w.n64 ? w.r64 : 0, w.n32 ? w.r32 : 0, 4);
 }
 
 int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
@@ -581,11 +581,13 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   CUtensorMap tmB;
   memset(&tmB, 0, sizeof(tmB));
   if (pair) {
-    // pair-format weights as 128 B rows: stage ks = [rank 0 half][rank 1 half], one box per (stage, rank)
-    const int rows_half = b_bytes / 128;
-    cuuint64_t dims[2] = {64, (cuuint64_t)p.ksteps * 2 * rows_half};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)rows_half};
+    // pair-format weights viewed as 512 B rows (the longest a box row can be: fewest TMA row requests):
+    // stage ks = [rank 0 half][rank 1 half], one box per (stage, rank)
+    SE_REQUIRE(b_bytes % 512 == 0 && b_bytes / 512 <= 256, "pair weight stage must be whole 512 B rows");
+    const int rows_half = b_bytes / 512;
+    cuuint64_t dims[2] = {256, (cuuint64_t)p.ksteps * 2 * rows_half};
+    cuuint64_t strides[1] = {512};
+    cuuint32_t box[2] = {256, (cuuint32_t)rows_half};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(L.w_pair), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

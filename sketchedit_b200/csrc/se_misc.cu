@@ -593,6 +593,46 @@ __global__ void cam_pack_v_tc_kernel(const T* __restrict__ f, uint8_t* __restric
   *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
+// Same image, bf16 input, built through shared memory: a block owns one (class, image, tap, 64-key unit); it reads
+// the 64 key pixels as contiguous channel vectors (coalesced 16 B loads; the kernel above reads 2 B at a 2-pixel
+// stride per key, a full sector per element), transposes in shared memory and writes whole 16 B swizzle chunks.
+__global__ void __launch_bounds__(256) cam_pack_v_tc_tile_kernel(const __nv_bfloat16* __restrict__ f, uint8_t* __restrict__ out, int B, int h, int w,
+                                                                 int C, int ws, int L, int Lpad, int r64, long long pc_bytes) {
+  constexpr int PITCH = 128 + 8;                       // bf16 elements per key row (C <= 128), 16 B aligned, odd multiple of 16 B
+  __shared__ __align__(16) __nv_bfloat16 tile[64][PITCH];
+  const int u64 = blockIdx.x, tap = blockIdx.y;
+  const int pc = blockIdx.z / B;
+  const long long b = blockIdx.z % B;
+  const int py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
+  const int C8n = C >> 3;
+  for (int idx = threadIdx.x; idx < 64 * C8n; idx += 256) {
+    const int key = idx / C8n, ch = idx - key * C8n;
+    const int l = u64 * 64 + key;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (l < L) {
+      const int ly = l / ws, lx = l - ly * ws;
+      q = *reinterpret_cast<const uint4*>(f + ((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(&tile[key][ch * 8]) = q;
+  }
+  __syncthreads();
+  const int NT = (C + 15) / 16 * 16, n64 = Lpad / 64;
+  const int ksteps = 4 * n64 / r64, sb = NT * r64 * 128;
+  const int u = tap * n64 + u64, ks = u / r64, j = u % r64;
+  uint8_t* base = out + (size_t)pc * pc_bytes + (size_t)b * ((size_t)ksteps * sb) + (size_t)ks * sb;
+  for (int idx = threadIdx.x; idx < C * 8; idx += 256) {
+    const int kc = idx & 7, c = idx >> 3;              // 8 key chunks of one channel row = one 128 B row of the image
+    uint32_t wds[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lo = *reinterpret_cast<const uint16_t*>(&tile[kc * 8 + 2 * k][c]);
+      const uint32_t hi = *reinterpret_cast<const uint16_t*>(&tile[kc * 8 + 2 * k + 1][c]);
+      wds[k] = lo | (hi << 16);
+    }
+    *reinterpret_cast<uint4*>(base + tc_b_image_offset(NT, r64, true, j, c, kc * 8)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+  }
+}
+
 // direct layout: fp32 [pc][b][tap][l (Ci = Lpad)][CoutP = C]
 template <typename T>
 __global__ void cam_pack_v_direct_kernel(const T* __restrict__ f, float* __restrict__ out, int B, int h, int w, int C, int ws, int L,
@@ -620,7 +660,11 @@ int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, in
     SE_REQUIRE(Lpad % 64 == 0, "Lpad % 64");
     if (C % 16) SE_CUDA_OK(cudaMemsetAsync(out, 0, 4 * pc_bytes, s));   // padded N rows
     const long long chunks = total / 8;
-    SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(chunks, 256), 256, 0, s>>>((const T*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes, chunks)));
+    if (dt == DT_BF16 && C % 8 == 0 && C <= 128 && 4LL * B <= 65535) {
+      cam_pack_v_tc_tile_kernel<<<dim3(Lpad / 64, 4, 4 * B), 256, 0, s>>>((const __nv_bfloat16*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes);
+    } else {
+      SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(chunks, 256), 256, 0, s>>>((const T*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes, chunks)));
+    }
   } else {
     SE_DISPATCH_T(dt, (cam_pack_v_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (float*)out, B, h, w, C, ws, L, Lpad, total)));
   }
@@ -683,7 +727,51 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, T* __r
   }
 }
 
+// rows of <= 1024 keys with 16 B aligned pitches: one WARP per row, the row lives in registers (32 values per lane,
+// float4 loads), reductions are shuffles only - no block barriers, one pass over the logits
+__global__ void __launch_bounds__(256) softmax_rows_warp_kernel(const float* __restrict__ S, int lds, __nv_bfloat16* __restrict__ P, int ldp, int L,
+                                                                long long rows) {
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* s4 = reinterpret_cast<const float4*>(S + row * lds);
+  float v[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = (k * 32 + lane) * 4;
+    float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (i < L) q = s4[k * 32 + lane];                  // i % 4 == 0 and the pitch covers the padded row
+    v[4 * k] = q.x;
+    v[4 * k + 1] = (i + 1 < L) ? q.y : -INFINITY;
+    v[4 * k + 2] = (i + 2 < L) ? q.z : -INFINITY;
+    v[4 * k + 3] = (i + 3 < L) ? q.w : -INFINITY;
+    mx = fmaxf(fmaxf(mx, v[4 * k]), fmaxf(fmaxf(v[4 * k + 1], v[4 * k + 2]), v[4 * k + 3]));
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    v[k] = expf(v[k] - mx);                             // exp(-inf) = 0 for the padding lanes
+    sum += v[k];
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  uint2* p2 = reinterpret_cast<uint2*>(P + row * ldp);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = (k * 32 + lane) * 4;
+    if (i < ldp) p2[k * 32 + lane] = make_uint2(pack_bf16x2(v[4 * k] * inv, v[4 * k + 1] * inv), pack_bf16x2(v[4 * k + 2] * inv, v[4 * k + 3] * inv));
+  }
+}
+
 int softmax_rows(const float* S, int lds, void* P, int dt, int ldp, long long rows, int L, cudaStream_t s) {
+  if (dt == DT_BF16 && L <= 1024 && lds % 4 == 0 && ldp % 4 == 0 && lds >= ((L + 3) & ~3) && ldp <= 1024 &&
+      (reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 7) == 0) {
+    softmax_rows_warp_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, s>>>(S, lds, (__nv_bfloat16*)P, ldp, L, rows);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   SE_DISPATCH_T(dt, (softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, s>>>(S, lds, (T*)P, ldp, L)));
   SE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -136,7 +136,9 @@ def test_inference_stream_matches_blocking_calls():
         batches.append({"image": img.pin_memory(), "mask": sk.pin_memory()})
     with torch.no_grad():
         want = [tuple(t.cpu() for t in model(d, mode="inference")) for d in batches]
-        got = list(model.inference_stream(iter(batches)))
+        got = [(c.clone(), m.clone()) for c, m in model.inference_stream(iter(batches))]   # results are ring views
+        fresh = list(model.inference_stream(iter(batches), pinned_ring=False))
     assert len(got) == len(want)
-    for (gc, gm), (wc, wm) in zip(got, want):
-        assert gc.is_pinned() and torch.equal(gc, wc) and torch.equal(gm, wm)
+    for (gc, gm), (fc, fm), (wc, wm) in zip(got, fresh, want):
+        assert torch.equal(gc, wc) and torch.equal(gm, wm)
+        assert fc.is_pinned() and torch.equal(fc, wc) and torch.equal(fm, wm)
