@@ -49,13 +49,15 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
+    PERIOD_MS = 25
+
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -274,7 +276,7 @@ def run_b200(args):
                 pass
         return comp, msk
 
-    run_stream(3)
+    run_stream(6)   # > depth + 2 batches: the pinned output ring is allocated (cudaHostAlloc is slow) before the timed loop
     e2e_value = world * B * args.steps / timed(lambda: run_stream(args.steps))
     clocks = sampler.stop() if rank == 0 else None
     h2d = B * 4 * H * W * 4

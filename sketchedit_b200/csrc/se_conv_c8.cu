@@ -302,18 +302,16 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool fast_epi = epi_fast_ok(p.e);
     const int row = q * 32 + lane;
     const int ry = row / C8_TW, rx = row % C8_TW;
-    int iter = 0;
     long long t_wacc = 0, t_begin = clock64();
-    int tx = blockIdx.x % p.tiles_x, ty = (blockIdx.x / p.tiles_x) % p.tiles_y, img = blockIdx.x / (p.tiles_x * p.tiles_y);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      if (tile != (int)blockIdx.x) {
-        tx += p.step_x;
-        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
-        ty += p.step_y;
-        if (ty >= p.tiles_y) { ty -= p.tiles_y; ++img; }
-        img += p.step_img;
-      }
-      if (epi_split == 1 && (iter & (TC_EPI_GROUPS - 1)) != grp) continue;      // tile-alternating groups
+    // tile-alternating groups (epi_split == 1) visit every TC_EPI_GROUPS-th tile of this CTA; a tile's coordinates
+    // come from two unsigned divisions (cheaper than stepping the mixed-radix counter through the skipped tiles)
+    const int istep = (epi_split == 1) ? TC_EPI_GROUPS : 1;
+    const uint32_t tpi = (uint32_t)(p.tiles_x * p.tiles_y);
+    for (int iter = (epi_split == 1) ? grp : 0, tile = blockIdx.x + iter * gridDim.x; tile < total_tiles;
+         tile += istep * gridDim.x, iter += istep) {
+      const uint32_t img_u = (uint32_t)tile / tpi, rem = (uint32_t)tile - img_u * tpi;
+      const uint32_t ty_u = rem / (uint32_t)p.tiles_x;
+      const int img = (int)img_u, ty = (int)ty_u, tx = (int)(rem - ty_u * (uint32_t)p.tiles_x);
       const int as = iter & (acc_stages - 1);
       const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
       const long long tw = p.dbg ? clock64() : 0;
@@ -515,6 +513,7 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   p.sbo_bytes = L.WR * 16;
   p.bias = c.bias;
   fill_epi(c, w.NT, &p.e);
+  SE_REQUIRE(c.out_dt != DT_BF16 || epi_addressable(c), "output tensor too large / misaligned for 32-bit block addressing");
   {
     // A-operand byte offsets inside the shared-memory region, per K unit (tile independent):
     // 64-wide units first (u = tap*n64 + chunk), then the 32-wide unit of each tap
@@ -551,6 +550,7 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   for (p.a_shift = 0; (1 << p.a_shift) < p.a_bufs; ++p.a_shift) {}
   int stages = stage_bytes ? (kSmemBudget - fixed) / stage_bytes : 1;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  { const char* cap = getenv("SE_C8_STAGES"); if (cap && atoi(cap) >= 2 && atoi(cap) < stages) stages = atoi(cap); }   // experiments
   SE_REQUIRE(stages >= (stage_bytes ? 2 : 1), "shared memory plan does not fit");
   p.num_stages = stages;
   const int smem_bytes = 1024 + fixed + stages * stage_bytes + (2 * TC_MAX_STAGES + 2 * C8_MAX_ABUFS + 9) * 8 + 16 + 3 * (p.NT + 32) * 4 + 64;

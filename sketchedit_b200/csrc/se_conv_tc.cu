@@ -289,6 +289,12 @@ void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
   e->Cout = c.Cout; e->NT = NT;
   e->goff = (c.epi == EPI_LINEAR) ? 0 : gated_goff(c.Cout);
 }
+// the fast epilogue addresses the output in 32-bit units of 16 B
+static inline bool epi_out_fits_u32(const ConvParams& c) {
+  const double units = c.out_c8 ? (double)c.N * c.ldo * c.Hout * c.Wout : (double)c.N * c.Hout * c.Wout * c.ldo / 8.0;
+  return units < 4294967296.0 && (reinterpret_cast<uintptr_t>(c.y) & 15) == 0;
+}
+bool epi_addressable(const ConvParams& c) { return epi_out_fits_u32(c); }
 
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes) {
   TcParams p;
@@ -318,6 +324,7 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   p.w = reinterpret_cast<const uint8_t*>(w.data);
   p.bias = c.bias;
   fill_epi(c, w.NT, &p.e);
+  SE_REQUIRE(c.out_dt != DT_BF16 || epi_addressable(c), "output tensor too large / misaligned for 32-bit block addressing");
   SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
   SE_REQUIRE(c.out_c8 != 2, "space-to-depth output is written by the channel-blocked kernel only");
   if (c.epi != EPI_LINEAR) {

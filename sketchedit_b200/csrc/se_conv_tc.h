@@ -58,6 +58,7 @@ struct TcParams {
 // pick (r64, r32) for a layer: as many units per stage as fit ~48 KB (SE_TC_STAGE_KB)
 void tc_choose_stage(TcWeights* w);
 void fill_epi(const ConvParams& c, int NT, EpiParams* e);
+bool epi_addressable(const ConvParams& c);   // output fits the fast epilogue's 32-bit (16 B unit) addressing
 int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes);
 int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream);
 

@@ -346,20 +346,21 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
   const int half = e.Cout >> 1, goff = e.goff;
   const int nb = (half + 7) >> 3;
   const uint32_t cs0 = smem_u32(cst);
-  __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(e.y);
-  size_t ostep;   // elements between consecutive 8-channel blocks of this pixel
+  // all addressing in 32-bit units of 16 B (one 8-channel block of one pixel); the launchers check the tensor is < 2^32 units
+  uint4* const ybase = reinterpret_cast<uint4*>(e.y);
+  uint32_t obase, ostep;   // this pixel's first block / distance between consecutive blocks
   if (e.out_c8 == 2) {
     // space-to-depth for a stride-2 consumer: [N][4 * ldo/4 blocks][Hout/2][Wout/2][8], parity (oy&1, ox&1) selects
     // the block group, so the consumer's taps become plain stride-1 reads of one parity each
-    const int Hs = e.Hout >> 1, Ws = e.Wout >> 1, par = ((oy & 1) << 1) | (ox & 1);
-    ostep = (size_t)Hs * Ws * 8;
-    obase += (((size_t)img * e.ldo + par * (e.ldo >> 2) + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws * 8 + (size_t)(ox >> 1) * 8;
+    const uint32_t Hs = e.Hout >> 1, Ws = e.Wout >> 1, par = ((oy & 1) << 1) | (ox & 1);
+    ostep = Hs * Ws;
+    obase = (((uint32_t)img * e.ldo + par * (e.ldo >> 2) + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws + (ox >> 1);
   } else if (e.out_c8) {
-    ostep = (size_t)e.Hout * e.Wout * 8;
-    obase += (((size_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout * 8 + (size_t)ox * 8;
+    ostep = (uint32_t)e.Hout * e.Wout;
+    obase = (((uint32_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout + ox;
   } else {
-    ostep = 8;
-    obase += (((size_t)img * e.Hout + oy) * e.Wout + ox) * e.ldo + e.choff;
+    ostep = 1;
+    obase = (((uint32_t)img * e.Hout + oy) * e.Wout + ox) * (e.ldo >> 3) + (e.choff >> 3);
   }
   // 4 outputs [c, c+4) from f[k..k+3], g[k..k+3]
   auto gate4 = [&](float* f, const float* g, int c, int k) {
@@ -378,9 +379,9 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     if (valid) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) gate4(f, g, c0 + 4 * q, 4 * q);
-      __nv_bfloat16* o = obase + (size_t)b * ostep;
-      *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(o + ostep) = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+      const uint32_t o = obase + (uint32_t)b * ostep;
+      ybase[o] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      ybase[o + ostep] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
     }
   };
   auto do8 = [&](int b) {
@@ -392,7 +393,7 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     if (valid) {
       gate4(f, g, c0, 0);
       gate4(f, g, c0 + 4, 4);
-      *reinterpret_cast<uint4*>(obase + (size_t)b * ostep) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      ybase[obase + (uint32_t)b * ostep] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
   };
   if (nsplit == 1) {
@@ -417,7 +418,7 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
         const int bb = grp + j * nsplit;
         gate4(f[j], g[j], bb * 8, 0);
         gate4(f[j], g[j], bb * 8 + 4, 4);
-        *reinterpret_cast<uint4*>(obase + (size_t)bb * ostep) =
+        ybase[obase + (uint32_t)bb * ostep] =
             make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]), pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
       }
     }
