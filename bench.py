@@ -288,7 +288,7 @@ def run_b200(args):
         if prec == "bf16" and tc_ms > 0:
             ach = tc_fl / (tc_ms / 1e3) / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-            roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv + attention GEMMs)",
+            roof = {"bound": "tensor", "kernel": "conv_c8_kernel + conv_tc_kernel (every tcgen05 implicit-GEMM launch: 71 gated convs on channel-blocked activations, 5 attention GEMM-conv launches)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % src,
                     "launches_timed": tc_n, "flops_convention": "algorithmic 2*MAC of the reference ops (SURVEY.md 8d), per launch summed",
