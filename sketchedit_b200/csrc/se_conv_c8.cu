@@ -51,7 +51,12 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, bool sw128) 
 // loads the halo of ITS tile but only HALF of each weight stage (rows [rank*NT/2, +NT/2) through the 2-D tensor map
 // tmB over the pair-format image), which halves the streamed-weight ingest that bounds the 96->192 layers, and the
 // leader issues one MMA for both tiles. Streaming (non-resident) layers only.
-template <int R64, int R32, int MMAS, int PAIR>
+//
+// KS1 = 1: the layer has ONE k-step per tile (resident weights + halo: r64/r32 are all its K units). Everything that
+// depends on the k-step index (A-offset table index, accumulate flag, last-step test, resident B address) is then a
+// compile-time constant, so the issue sequence is just "constant-bank offset + base -> descriptor -> MMA": the
+// indexed constant loads of the generic form (~100+ cycles each, on the critical path of a 15-18 MMA tile) disappear.
+template <int R64, int R32, int MMAS, int PAIR, int KS1 = 0>
 __global__ void __launch_bounds__(TC_NUM_THREADS, 1)
 conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const C8Params p) {
   constexpr bool kPair = PAIR != 0;
@@ -76,17 +81,22 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* a_full = empty_bar + TC_MAX_STAGES;
   uint64_t* a_empty = a_full + C8_MAX_ABUFS;
   uint64_t* tmem_full = a_empty + C8_MAX_ABUFS;
-  uint64_t* tmem_empty = tmem_full + 4;
-  uint64_t* wres_bar = tmem_empty + 4;
-  // accumulator ring: N <= 128 leaves room for 4 TMEM stages; the two epilogue groups then drain alternate tiles
-  // (each group gets twice the time per tile); wider tiles keep 2 stages and split a tile's columns between groups
-  const int acc_stages = p.NT <= 128 ? 4 : 2;
-  const int acc_stride = p.NT <= 128 ? 128 : 256;
-  const int epi_split = acc_stages == 4 ? 1 : TC_EPI_GROUPS;
+  uint64_t* tmem_empty = tmem_full + 8;
+  uint64_t* wres_bar = tmem_empty + 8;
+  // accumulator ring: N <= 128 leaves room for 4 TMEM stages: the four epilogue groups drain alternate tiles (a group
+  // has four tile-times per tile); wider tiles keep 2 stages and split a tile's columns between the groups.
+  // N <= 64 even fits 8 stages, two per group: while a group drains tile i the MMAs of tile i+4 already fill its second
+  // stage, so a group's cycle is the drain alone instead of drain + MMA latency (the small-N layers are epilogue bound)
+  const int acc_shift = p.NT <= 64 ? 3 : (p.NT <= 128 ? 2 : 1);
+  const int acc_stages = 1 << acc_shift;
+  const int acc_stride = 512 >> acc_shift;
+  const int epi_split = acc_stages >= 4 ? 1 : TC_EPI_GROUPS;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(wres_bar + 1);
   float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 16 B aligned: read with ld.shared.v4
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform by construction (a shuffle from lane 0): lets the compiler keep role-dependent values - the tile
+  // parity of the second MMA issuer, ring indices, descriptors - on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -99,7 +109,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kPair ? 2 * 4 * epi_split : 128 * epi_split);   // pair: one arrive per epilogue warp of both CTAs
     }
@@ -120,7 +130,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();       // pair: the peer's barriers must exist before any remote signal
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // uniform copy (feeds MMA / tcgen05.ld addresses)
 
   const int total_tiles = p.N * p.tiles_x * p.tiles_y;
   const int ksteps = p.ksteps;
@@ -214,7 +224,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       if (dual && (iter & 1) != me) continue;
       const int as = iter & (acc_stages - 1);
-      const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
+      const uint32_t accphase = (iter >> acc_shift) & 1;
       long long tw = p.dbg ? clock64() : 0;
       if (kPair) mbar_wait_cluster(&tmem_empty[as], accphase ^ 1, 2); else mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
       if (p.dbg) t_wtmem += clock64() - tw;
@@ -226,7 +236,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * acc_stride;
-      for (int ks = 0; ks < ksteps; ++ks) {
+      for (int ks = 0; ks < (KS1 ? 1 : ksteps); ++ks) {
         if (staged) {
           tw = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase, 3);
@@ -235,11 +245,11 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // shared-window addresses as plain 32-bit integer arithmetic on the (constant) window base: stays uniform
         const uint32_t st = smem_base + off_stages + (uint32_t)stage * stage_bytes;
-        const uint32_t sB = p.resident ? smem_base + off_wres + (uint32_t)ks * b_bytes : st + stage_a;
+        const uint32_t sB = p.resident ? smem_base + off_wres + (KS1 ? 0u : (uint32_t)ks * b_bytes) : st + stage_a;
         const uint32_t sA = halo ? smem_base + (uint32_t)ab * p.a_bytes : st;
         {
           const uint32_t lead = elect_one() ? 1u : 0u;   // predicate only: no divergent region around the issue loop
-          uint32_t acc = ks ? 1u : 0u;
+          uint32_t acc = (!KS1 && ks) ? 1u : 0u;
           // descriptors: only the 14-bit start-address field (bytes >> 4) changes between MMAs
           const uint32_t a_lo = ((p.lbo_bytes >> 4) & 0x3FFF) << 16;
           const uint32_t a_hi = ((p.sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
@@ -247,7 +257,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t kstep16 = p.kstep_bytes >> 4;
           const uint32_t n_u64 = p.ntaps * p.n64;
           // A offsets come from the constant bank (compile-time indices when the k-step structure is templated)
-          const int u0 = ks * r64, v0 = n_u64 + ks * r32;
+          const int u0 = KS1 ? 0 : ks * r64, v0 = KS1 ? R64 : (int)n_u64 + ks * r32;
 #pragma unroll
           for (int j = 0; j < (R64 >= 0 ? R64 : 32); ++j) {
             if (j < r64) {
@@ -278,13 +288,13 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (kPair) {
             if (staged) umma2_commit_if(lead, &empty_bar[stage]);
-            if (ks == ksteps - 1) {
+            if (KS1 || ks == ksteps - 1) {
               if (halo) umma2_commit_if(lead, &a_empty[ab]);
               umma2_commit_if(lead, &tmem_full[as]);
             }
           } else {
             if (staged) umma_commit_if(lead, &empty_bar[stage]);
-            if (ks == ksteps - 1) {
+            if (KS1 || ks == ksteps - 1) {
               if (halo) umma_commit_if(lead, &a_empty[ab]);
               umma_commit_if(lead, &tmem_full[as]);
             }
@@ -313,7 +323,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ty_u = rem / (uint32_t)p.tiles_x;
       const int img = (int)img_u, ty = (int)ty_u, tx = (int)(rem - ty_u * (uint32_t)p.tiles_x);
       const int as = iter & (acc_stages - 1);
-      const uint32_t accphase = (acc_stages == 4 ? (iter >> 2) : (iter >> 1)) & 1;
+      const uint32_t accphase = (iter >> acc_shift) & 1;
       const long long tw = p.dbg ? clock64() : 0;
       mbar_wait(&tmem_full[as], accphase, 4);
       if (p.dbg) t_wacc += clock64() - tw;
@@ -429,12 +439,17 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
 // k-step structures of the streamed-weight layers that run as CTA pairs (96->192: <1,1>; 192/48->192: <1,0>;
 // the 48->96 stride-2 layer of the refine branch: <3,0>)
 #define C8_PAIR_SPECIALISATIONS(X) X(1, 0, 4) X(1, 1, 4) X(3, 0, 4)
+// structures that occur with a single k-step per tile (resident weights): compile-time k-step index (KS1)
+#define C8_KS1_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(4, 4, 4) X(4, 0, 4)
 static int c8_set_smem_attr(int bytes) {
 #define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   C8_SPECIALISATIONS(X)
 #undef X
 #define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   C8_PAIR_SPECIALISATIONS(X)
+#undef X
+#define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  C8_KS1_SPECIALISATIONS(X)
 #undef X
   SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<-1, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return 0;
@@ -463,6 +478,16 @@ static int c8_dispatch(const C8Params& p, const CUtensorMap& tmA, const CUtensor
     C8_PAIR_SPECIALISATIONS(X)
 #undef X
     SE_REQUIRE(false, "no CTA-pair instantiation for this k-step structure");
+  }
+  static const bool no_ks1 = getenv("SE_C8_NOKS1") != nullptr;   // A/B switch for experiments
+  if (p.ksteps == 1 && p.resident && p.mode == C8_HALO && !no_ks1) {
+#define X(a, b, m)                                                                             \
+    if (p.r64 == a && p.r32 == b && (a == 0 || p.mmas64 == m)) {                               \
+      conv_c8_kernel<a, b, m, 0, 1><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p); \
+      return 0;                                                                                \
+    }
+    C8_KS1_SPECIALISATIONS(X)
+#undef X
   }
 #define X(a, b, m)                                                                             \
   if (p.r64 == a && p.r32 == b && (a == 0 || p.mmas64 == m)) {                                 \
@@ -553,7 +578,7 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   { const char* cap = getenv("SE_C8_STAGES"); if (cap && atoi(cap) >= 2 && atoi(cap) < stages) stages = atoi(cap); }   // experiments
   SE_REQUIRE(stages >= (stage_bytes ? 2 : 1), "shared memory plan does not fit");
   p.num_stages = stages;
-  const int smem_bytes = 1024 + fixed + stages * stage_bytes + (2 * TC_MAX_STAGES + 2 * C8_MAX_ABUFS + 9) * 8 + 16 + 3 * (p.NT + 32) * 4 + 64;
+  const int smem_bytes = 1024 + fixed + stages * stage_bytes + (2 * TC_MAX_STAGES + 2 * C8_MAX_ABUFS + 17) * 8 + 16 + 3 * (p.NT + 32) * 4 + 64;
 
   EncodeTiledFn enc = c8_encode_fn();
   SE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");

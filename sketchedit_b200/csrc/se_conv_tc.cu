@@ -63,7 +63,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 16 B aligned: read with ld.shared.v4
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform by construction (a shuffle from lane 0): lets the compiler keep role-dependent values - the tile
+  // parity of the second MMA issuer, ring indices, descriptors - on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -91,7 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // uniform copy (feeds MMA / tcgen05.ld addresses)
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.N * tiles_per_img * p.n_tiles;
