@@ -72,6 +72,7 @@ struct ConvParams {
   const void* w;        // layout depends on the kernel (see se_conv_direct.cu / se_conv_tc.cu)
   long long w_img_stride;   // elements between images (0 = shared)
   const float* bias;    // [Cout] or nullptr
+  const float* bias_host;   // optional host copy of bias: lets the tensor-core kernels pass the epilogue constants as kernel parameters
   int Cout;             // pre-gate output channels (GEMM N, real)
   // output
   void* y;

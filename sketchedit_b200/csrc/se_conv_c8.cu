@@ -211,18 +211,21 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // per-tile protocol (two commits, two barrier waits, fence, descriptor set-up: ~600 cycles measured) is longer
     // than the 3-4 queued MMAs of a small-N layer (40-56 cycles each) can cover, so the tensor pipe would idle
     // between tiles. Warps 1 and 3 therefore issue alternate tiles: each one's protocol overlaps the other's burst.
-    const bool dual = !staged;
-    const int me = (warp == 3) ? 1 : 0;
+    // The issuer count must divide every ring it indexes (TMEM stages, halo buffers): a ring slot is then always
+    // handled by the same warp, in order - with slots shared between issuers a warp could test a barrier two phases
+    // ahead, and mbarrier parity waits alias modulo 2 (a 3-issuer experiment corrupted tiles and hung exactly so).
+    const int n_issuers = (!staged && (p.a_bufs & 1) == 0 && (acc_stages & 1) == 0) ? 2 : 1;
+    const int me = (warp == 3) ? 1 : 0;   // a second issuer that is not needed simply finds no tile below
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
-    int stage = 0, iter = 0;
+    int stage = 0;
     uint32_t phase = 0;
     long long t_wfull = 0, t_wtmem = 0, t_whalo = 0, t_begin = clock64();
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t off_wres = halo ? (uint32_t)(p.a_bufs * p.a_bytes) : 0u;
     const uint32_t off_stages = off_wres + (p.resident ? (uint32_t)p.wres_bytes : 0u);
     if (p.resident) mbar_wait(wres_bar, 0, 6);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      if (dual && (iter & 1) != me) continue;
+    for (int iter = me, tile = (me < n_issuers) ? (int)(blockIdx.x + me * gridDim.x) : total_tiles; tile < total_tiles;
+         tile += n_issuers * gridDim.x, iter += n_issuers) {
       const int as = iter & (acc_stages - 1);
       const uint32_t accphase = (iter >> acc_shift) & 1;
       long long tw = p.dbg ? clock64() : 0;
@@ -331,7 +334,13 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_stride;
       const int py = ty * C8_TH + ry, px = tx * C8_TW + rx;
       const bool valid = (py < p.Ho) && (px < p.Wo);
-      if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
+      if (KS1 && p.ecst_nb) {   // (only the single-k-step instantiations carry this code: the launcher sets ecst_nb for them alone)
+        // constants as kernel parameters (gated, bf16 block output, 2 or 3 blocks, one group per tile)
+        const int oy = py * p.e.osy + p.e.ooy, ox = px * p.e.osx + p.e.oox;
+        const bool elu = (p.e.epi == EPI_GATE_ELU);
+        if (p.ecst_nb == 3) { if (elu) tc_epilogue_gated_const<true, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); else tc_epilogue_gated_const<false, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); }
+        else { if (elu) tc_epilogue_gated_const<true, 2>(p.e, p.ecst, taddr, img, valid, oy, ox); else tc_epilogue_gated_const<false, 2>(p.e, p.ecst, taddr, img, valid, oy, ox); }
+      } else if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
       else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
       tc_fence_before();
       if (kPair) {
@@ -539,6 +548,23 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   p.bias = c.bias;
   fill_epi(c, w.NT, &p.e);
   SE_REQUIRE(c.out_dt != DT_BF16 || epi_addressable(c), "output tensor too large / misaligned for 32-bit block addressing");
+  {
+    // epilogue constants as kernel parameters when the tile is drained by one group and has 2 or 3 blocks (N <= 48: the
+    // 256^2 / 128^2 layers; with 6 blocks the two-pass form measured slower than the shared-memory constants)
+    static const bool no_ecst = getenv("SE_C8_NOECST") != nullptr;   // A/B switch for experiments
+    const int half = c.Cout / 2, nb = (half + 7) / 8;
+    p.ecst_nb = 0;
+    if (!no_ecst && c.epi != EPI_LINEAR && c.bias_host != nullptr && epi_fast_ok(p.e) && w.NT <= 128 && (nb == 2 || nb == 3) &&
+        tc_ksteps(w) == 1 && L.resident && L.mode == C8_HALO) {
+      p.ecst_nb = nb;
+      for (int i = 0; i < 24; ++i) {
+        const float bf = i < half ? c.bias_host[i] : 0.0f, bg = i < half ? c.bias_host[half + i] : 0.0f;
+        p.ecst[0][i] = bf;
+        p.ecst[1][i] = bf * 1.4426950408889634f;
+        p.ecst[2][i] = 0.5f * bg;
+      }
+    }
+  }
   {
     // A-operand byte offsets inside the shared-memory region, per K unit (tile independent):
     // 64-wide units first (u = tap*n64 + chunk), then the 32-wide unit of each tap

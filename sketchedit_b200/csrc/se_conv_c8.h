@@ -38,6 +38,11 @@ struct C8Params {
   int num_stages, resident, wres_bytes;
   const float* bias;
   EpiParams e;
+  // gated layers with <= 24 outputs (the N <= 48 layers at 256^2 / 128^2): epilogue constants by accumulator column as kernel parameters,
+  // [0] bias of feature c, [1] bias * log2(e), [2] 0.5 * bias of gate c; with a compile-time column count they become
+  // constant-bank operands of the FMAs (no shared-memory loads in the epilogue). ecst_nb = 8-column blocks, 0 = unused
+  int ecst_nb;
+  float ecst[3][24];
   unsigned long long* dbg;
 };
 

@@ -534,7 +534,7 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
       memcpy(cp.tap_cb, cw.c8cb, sizeof(cp.tap_cb));
     }
     cp.w = nullptr; cp.w_img_stride = 0;
-    cp.bias = L.bias; cp.Cout = s.cout;
+    cp.bias = L.bias; cp.bias_host = L.b_host.data(); cp.Cout = s.cout;
     cp.y = out; cp.out_dt = c.act_dt();
     cp.Hout = Ho * cw.osy; cp.Wout = Wo * cw.osx; cp.ldo = ldo; cp.choff = choff;
     cp.osy = cw.osy; cp.ooy = cw.ooy; cp.osx = cw.osx; cp.oox = cw.oox;

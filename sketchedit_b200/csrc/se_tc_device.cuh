@@ -427,6 +427,53 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
   }
 }
 
+// Same epilogue for a whole tile of NB 8-column blocks with the constants in KERNEL PARAMETER space: NB is compile
+// time, so every constant is an immediate constant-bank operand of its FMA/FADD and the epilogue issues no shared-memory
+// loads (ncu: the first use of each LDS'd constant was the top stall of the small-N layers, short scoreboard).
+// All TMEM loads of the tile are issued before the single wait.
+template <bool kElu, int NB>
+__device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, const float (&cst)[3][24], uint32_t taddr, int img, bool valid, int oy,
+                                                        int ox) {
+  const int goff = e.goff;
+  uint4* const ybase = reinterpret_cast<uint4*>(e.y);
+  uint32_t obase, ostep;
+  if (e.out_c8 == 2) {
+    const uint32_t Hs = e.Hout >> 1, Ws = e.Wout >> 1, par = ((oy & 1) << 1) | (ox & 1);
+    ostep = Hs * Ws;
+    obase = (((uint32_t)img * e.ldo + par * (e.ldo >> 2) + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws + (ox >> 1);
+  } else if (e.out_c8) {
+    ostep = (uint32_t)e.Hout * e.Wout;
+    obase = (((uint32_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout + ox;
+  } else {
+    ostep = 1;
+    obase = (((uint32_t)img * e.Hout + oy) * e.Wout + ox) * (e.ldo >> 3) + (e.choff >> 3);
+  }
+  static_assert(NB <= 3, "one pass of at most three blocks (16 registers per block)");
+  constexpr int PASS = NB;
+#pragma unroll
+  for (int b0 = 0; b0 < NB; b0 += PASS) {
+    float f[PASS][8], g[PASS][8];
+#pragma unroll
+    for (int j = 0; j < PASS; ++j) {
+      tmem_ld8(taddr + (b0 + j) * 8, f[j]);
+      tmem_ld8(taddr + goff + (b0 + j) * 8, g[j]);
+    }
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < PASS; ++j) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = (b0 + j) * 8 + k;                // compile time
+          f[j][k] = gate_one<kElu>(f[j][k], g[j][k], cst[0][c], cst[1][c], cst[2][c]);
+        }
+        ybase[obase + (uint32_t)(b0 + j) * ostep] =
+            make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]), pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
+      }
+    }
+  }
+}
+
 // Drain one accumulator tile (this thread = TMEM lane = one output position) and apply the fused epilogue.
 //   gated : out[c] = act(acc[c] + b[c]) * sigmoid(acc[goff + c] + b[Cout/2 + c])
 //   linear: out[c] = (acc[c] + b[c]) * scale * colscale[img][c]
