@@ -248,7 +248,11 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
     // the exact (swizzled) shared-memory image of every pipeline stage, see se_conv_tc.h
     const int ksteps = tc_ksteps(tc), sb = tc_stage_b_bytes(tc);
     std::vector<uint16_t> img((size_t)ksteps * sb / 2, 0);
-    auto wv = [&](int t, int ci, int n) -> uint16_t { return ci < Ci ? f32_to_bf16_rn(weff[((size_t)t * Ci + ci) * Cout + n]) : (uint16_t)0; };
+    // gate channels (n >= Cout/2) are stored pre-multiplied by 0.5 (exact in bf16): the accumulator then holds 0.5*g and
+    // the epilogue's sigmoid(g + b) = 0.5*tanh(0.5*g + 0.5*b) + 0.5 needs one add (with a constant operand) before the MUFU
+    auto wv = [&](int t, int ci, int n) -> uint16_t {
+      return ci < Ci ? f32_to_bf16_rn(weff[((size_t)t * Ci + ci) * Cout + n] * (n >= Cout / 2 ? 0.5f : 1.0f)) : (uint16_t)0;
+    };
     for (int ks = 0; ks < ksteps; ++ks) {
       uint16_t* base = img.data() + (size_t)ks * sb / 2;
       for (int j = 0; j < tc.r64 && tc.n64; ++j) {

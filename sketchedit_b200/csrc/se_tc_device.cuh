@@ -320,19 +320,21 @@ __device__ __forceinline__ void epi_fill_constants(float* cst, int n, const floa
 }
 
 // one gated output: act(f + b) * sigmoid(g + b')  (reference utils.py:29-32)
-//   sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 (one MUFU); ELU's exp as ex2 with the bias folded into the FMA
-template <bool kElu>
-__device__ __forceinline__ float gate_one(float f, float g, float b, float bl, float hb) {
+//   sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 (one MUFU); the accumulator column of a gate already holds 0.5 * g (the gate
+//   weights are packed pre-multiplied by 0.5), hb = 0.5 * b'. ELU's exp as ex2: with the bias folded into the FMA (bl =
+//   b * log2 e), or, kNoBl, as (f + b) * log2 e so that no third constant is needed (constant-bank epilogue).
+template <bool kElu, bool kNoBl = false>
+__device__ __forceinline__ float gate_one(float f, float ghalf, float b, float bl, float hb) {
   const float fv = f + b;
   float a;
   if (kElu) {
-    const float ex = ex2_approx(fmaf(f, 1.4426950408889634f, bl)) - 1.0f;
+    const float ex = ex2_approx(kNoBl ? fv * 1.4426950408889634f : fmaf(f, 1.4426950408889634f, bl)) - 1.0f;
     a = fv > 0.0f ? fv : ex;
   } else {
     a = fmaxf(fv, 0.0f);
   }
   const float h = 0.5f * a;
-  return fmaf(h, tanh_approx(fmaf(g, 0.5f, hb)), h);
+  return fmaf(h, tanh_approx(ghalf + hb), h);
 }
 
 // Gated epilogue of one accumulator tile, minimal-instruction form (epi_fast_ok): work is cut in 8-column channel
@@ -465,7 +467,7 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int c = (b0 + j) * 8 + k;                // compile time
-          f[j][k] = gate_one<kElu>(f[j][k], g[j][k], cst[0][c], cst[1][c], cst[2][c]);
+          f[j][k] = gate_one<kElu, true>(f[j][k], g[j][k], cst[0][c], 0.0f, cst[2][c]);   // both constants: immediate constant-bank operands
         }
         ybase[obase + (uint32_t)(b0 + j) * ostep] =
             make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]), pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
