@@ -163,6 +163,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# one ncu capture of the dominant kernel at the default workload (profiles/r01_dram_traffic_b128.md): 101.3 MB read + 60.8 MB written
+DOMINANT_KERNEL_DRAM_BYTES = 162.1e6
+
+
 def run_b200(args):
     import torch.distributed as dist
     from argparse import Namespace
@@ -289,7 +293,9 @@ def run_b200(args):
             ach = tc_fl / (tc_ms / 1e3) / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
             roof = {"bound": "tensor", "kernel": "conv_c8_kernel + conv_tc_kernel (every tcgen05 implicit-GEMM launch: 71 gated convs on channel-blocked activations, 5 attention GEMM-conv launches)",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": DOMINANT_KERNEL_DRAM_BYTES if (B == 128 and prec == "bf16") else None,
+                    "traffic_note": "dram__bytes_read+write per launch of conv_c8_kernel<1,1,4,PAIR> (96->192, 31 launches/step) at batch 128 from one ncu capture (profiles/r01_dram_traffic_b128.md); algorithmic bytes of that launch: 201.7e6",
                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % src,
                     "launches_timed": tc_n, "flops_convention": "algorithmic 2*MAC of the reference ops (SURVEY.md 8d), per launch summed",
                     "kernel_share_of_step": tc_ms / ms}
