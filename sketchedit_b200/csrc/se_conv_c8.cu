@@ -472,8 +472,7 @@ static bool c8_pair_kernel_exists(int r64, int r32, int mmas64) {
 static int c8_dispatch(const C8Params& p, const CUtensorMap& tmA, const CUtensorMap& tmB, bool pair, int grid, int smem_bytes,
                        cudaStream_t stream) {
   if (pair) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_NUM_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
