@@ -11,7 +11,11 @@
 //   * 5x5 stems over the 8-channel packed input: GEMM-K runs over the pixel window (LBO = 16 B): 5 taps x 3 MMAs.
 // The B operand (weights) is the pre-swizzled stage image of se_conv_tc.h, either streamed per k-step with
 // cp.async.bulk or, when the whole layer fits (<= ~112 KB), loaded once and kept resident in shared memory.
-// Warp roles, TMEM double buffering and the fused epilogue are those of se_conv_tc.cu.
+//   * stride-2 3x3 layers read a SPACE-TO-DEPTH C8 tensor (written that way by the producer's epilogue): every tap is a
+//     stride-1 read of one parity group, selected by a per-tap channel-block offset (C8Layer::tap_cb).
+// Streamed-weight layers with N = 192 / 96 run as CTA PAIRS (cta_group::2, M = 256): each CTA loads half of every weight
+// stage. 640 threads: warp 0 producer, warp 1 (+3 on resident layers) MMA issue, warp 2 TMEM allocation, warps 4-19 four
+// epilogue groups; 2 / 4 / 8 TMEM accumulator stages for N <= 256 / 128 / 64. The fused epilogue lives in se_tc_device.cuh.
 #include "se_conv_c8.h"
 
 #include <stdlib.h>
