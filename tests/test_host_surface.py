@@ -1,0 +1,63 @@
+"""Host-side mirror of the reference's inference surface (no GPU): the test_celeb.sh command line parses, the module /
+class / attribute names the reference's checkpoints and scripts rely on exist, and the dataset reads the reference's
+list format."""
+import os
+import re
+import shlex
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _script_args(name):
+    txt = open(os.path.join(ROOT, name)).read().replace("\\\n", " ")
+    argv = shlex.split(txt)
+    assert argv[:2] == ["python", "test.py"]
+    return argv[2:]
+
+
+def test_reference_command_lines_parse():
+    from options.test_options import TestOptions
+    for script in ("test_celeb.sh", "test_places.sh"):
+        opt = TestOptions().parse(_script_args(script) + ["--gpu_ids", "-1"])
+        assert opt.model == "editline2" and opt.netG == "deepfillc2" and opt.use_cam and opt.pool_type == "max"
+        assert opt.isTrain is False and opt.gpu_ids == [] and opt.precision in ("bf16", "fp32")
+
+
+def test_module_surface_and_state_dict_keys():
+    """Same class names / constructor path / parameter names as the reference (strict checkpoint loading depends on it)."""
+    from options.test_options import TestOptions
+    import models
+    from sketchedit_b200 import synth
+    from sketchedit_b200.arch import NET_LAYERS
+    opt = TestOptions().parse(_script_args("test_celeb.sh") + ["--gpu_ids", "-1"])
+    opt.isSkip = True                                   # the reference's own escape hatch: do not look for checkpoints
+    model = models.create_model(opt)
+    assert type(model).__name__ == "EditLine2Model"
+    assert type(model.netM).__name__ == "MDGenerator" and type(model.netG).__name__ == "DeepFillC2Generator"
+    for net, mod in (("M", model.netM), ("G", model.netG)):
+        keys = set(mod.state_dict().keys())
+        want = set()
+        for L in NET_LAYERS[net]:
+            want |= {L.name + ".weight", L.name + ".bias"}
+        assert keys == want, (net, sorted(keys ^ want)[:6])
+        # the synthetic checkpoints load strictly into the UNMODIFIED reference (oracle/make_golden.py): same key set
+        assert keys == set(synth.synth_state_dict(net).keys())
+    for attr in ("forward", "inference_stream", "engine", "preprocess_input", "initialize_networks"):
+        assert callable(getattr(model, attr))
+
+
+def test_inference_requires_the_gpu_path():
+    """No CPU fallback behind the module surface either."""
+    import pytest
+    from argparse import Namespace
+    import models
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    opt = Namespace(gpu_ids=[], isTrain=False, isSkip=True, netG="deepfillc2", init_type="xavier", init_variance=0.02, use_cam=True,
+                    pool_type="max", no_mask_cc=False, no_mask_coarse=False, joint_train_inp=True, model="editline2", precision="bf16")
+    model = models.create_model(opt)
+    data = {"image": torch.zeros(1, 3, 64, 64), "mask": torch.zeros(1, 1, 64, 64)}
+    with pytest.raises(Exception):
+        model(data, mode="inference")
