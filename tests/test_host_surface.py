@@ -61,3 +61,38 @@ def test_inference_requires_the_gpu_path():
     data = {"image": torch.zeros(1, 3, 64, 64), "mask": torch.zeros(1, 1, 64, 64)}
     with pytest.raises(Exception):
         model(data, mode="inference")
+
+
+def test_testimage_dataset_reads_the_reference_list_format(tmp_path):
+    """data.create_dataloader on a list file: [-1,1] RGB image, sketch resized to the image and binarised with > 0,
+    output name = list entry (reference data/testimage_dataset.py:60-111)."""
+    import numpy as np
+    from PIL import Image
+    from options.test_options import TestOptions
+    import data
+    idir, mdir, odir = tmp_path / "images", tmp_path / "edges", tmp_path / "out"
+    idir.mkdir(); mdir.mkdir()
+    rng = np.random.RandomState(0)
+    names = ["a_00", "b_01", "c_02"]
+    imgs = {}
+    for n in names:
+        imgs[n] = rng.randint(0, 256, (64, 48, 3), dtype=np.uint8)
+        Image.fromarray(imgs[n]).save(idir / (n + ".png"))
+        edge = np.zeros((32, 24), np.uint8)               # half resolution: must be resized to the image size
+        edge[8:12, 4:20] = 255
+        Image.fromarray(edge).save(mdir / (n + ".png"))
+    (tmp_path / "list.txt").write_text("".join(n + ".png\n" for n in names))
+    argv = _script_args("test_celeb.sh") + ["--gpu_ids", "-1", "--image_dirs", str(idir), "--mask_dirs", str(mdir),
+                                            "--image_lists", str(tmp_path / "list.txt"), "--output_dir", str(odir), "--batchSize", "1"]
+    opt = TestOptions().parse(argv)
+    loader = data.create_dataloader(opt)
+    seen = []
+    for item in loader:
+        assert item["image"].shape == (1, 3, 64, 48) and item["mask"].shape == (1, 1, 64, 48)
+        n = item["path"][0].replace(".png", "")
+        want = torch.from_numpy(imgs[n]).permute(2, 0, 1).float().div(255).sub(0.5).div(0.5)
+        assert torch.equal(item["image"][0], want)
+        assert set(item["mask"].unique().tolist()) <= {0.0, 1.0} and item["mask"].sum() > 0
+        seen.append(n)
+    assert seen == names                                  # serial_batches: list order
+    assert os.path.isdir(odir)
