@@ -13,13 +13,14 @@ from PIL import Image
 class TestImageDataset(torch.utils.data.Dataset):
     @staticmethod
     def modify_commandline_options(parser, is_train):
-        parser.add_argument("--image_dirs", type=str, required=False, default="./datasets/face_release/images")
-        parser.add_argument("--mask_dirs", type=str, required=False, default="./datasets/face_release/edges")
-        parser.add_argument("--image_lists", type=str, required=False, default="./datasets/face_release/list.txt")
-        parser.add_argument("--image_postfix", type=str, default=".png")
+        # same required flags and defaults as the reference (data/testimage_dataset.py:16-32)
+        parser.add_argument("--image_dirs", type=str, required=True)
+        parser.add_argument("--mask_dirs", type=str, required=True)
+        parser.add_argument("--image_lists", type=str, required=True)
+        parser.add_argument("--image_postfix", type=str, default=".jpg")
         parser.add_argument("--mask_postfix", type=str, default=".png")
         parser.add_argument("--output_labels", type=str, required=False, help="';'-separated prefixes for output names")
-        parser.add_argument("--output_dir", type=str, required=False, default="./results")
+        parser.add_argument("--output_dir", type=str, required=True)
         parser.add_argument("--output_mask_dir", type=str, required=False)
         return parser
 
@@ -33,7 +34,7 @@ class TestImageDataset(torch.utils.data.Dataset):
         for i, (idir, mdir, lst) in enumerate(zip(opt.image_dirs.split(";"), opt.mask_dirs.split(";"),
                                                   opt.image_lists.split(";"))):
             with open(lst) as f:
-                stems = [ln.strip("\n").replace(opt.image_postfix, "") for ln in f if ln.strip()]
+                stems = [ln.strip("\n").replace(opt.image_postfix, "") for ln in f]                   # every line is an entry, like the reference (:74-76)
             for s in stems:
                 out = (labels[i] + "_" if labels else "") + s + opt.image_postfix
                 self.items.append((os.path.join(idir, s + opt.image_postfix), os.path.join(mdir, s + opt.mask_postfix), out))

@@ -62,12 +62,19 @@ int se_forward_inference(se_model* m, const float* image, const float* sketch, i
                          float* composed, float* mask, float* coarse, float* fine, float* mask_image,
                          const float* mask_bin_in, float* mask_bin_out, void* stream);
 
+/* Same forward, outputs written as ONE packed tensor [B,4,H,W] (channels 0-2 composed, channel 3 the soft mask): the
+ * layout of the data-parallel output all-gather (`[B/n,4,H,W]` shards), so a rank's heads write straight
+ * into its slice of the gather buffer and no pack/concat pass exists. */
+int se_forward_inference_packed(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision,
+                                float* packed, void* stream);
+
 /* ---- netM: replaces MDGenerator.forward(x, guide) -> (mask1, x_stage1)  (editline2_g.py:59-94) */
 int se_netM_forward(se_model* m, const float* x, const float* guide, int B, int H, int W, int precision, float* mask1,
                     float* x_stage1 /* may be NULL */, void* stream);
 
 /* ---- netG: replaces DeepFillC2Generator.forward(x, x2, mask, mask2, guide) -> (x_stage1, x_stage2)
- *      (editline_g.py:119-221). mask / mask2 [B,1,H,W]. */
+ *      (editline_g.py:119-221). mask / mask2 [B,1,H,W]. guide may be NULL = the reference's guide=None (an all-ones
+ *      sketch channel, editline_g.py:127-130). */
 int se_netG_forward(se_model* m, const float* x, const float* x2, const float* mask, const float* mask2, const float* guide,
                     int B, int H, int W, int precision, float* x_stage1, float* x_stage2, void* stream);
 
@@ -92,10 +99,12 @@ int se_outputs_to_uint8(const float* composed, const float* mask, int B, int H, 
 int se_last_launch_count(void);
 /* bytes of device workspace currently held by the model's arena */
 long long se_workspace_bytes(se_model* m);
-/* when set (default 0), the dominant tcgen05 kernel launches are bracketed by CUDA events on their
- * stream; se_tc_time_ms returns the summed duration (ms) and launch count since the last reset. */
-int se_tc_timing_enable(int on);
-int se_tc_time_ms(double* ms, int* launches, double* flops);
+/* when set (default 0), every kernel launch of the forward calls is bracketed by CUDA events on its stream and
+ * accounted to a kernel class (kernel + layer shape) with its algorithmic FLOPs / bytes. se_timing_report writes a
+ * JSON table of the classes seen since the last se_timing_enable(1) into buf (returns the length needed, -1 on error).
+ * Throughput must be measured with timing OFF; bench.py runs one separate instrumented pass for its roofline table. */
+int se_timing_enable(int on);
+int se_timing_report(char* buf, int cap);
 
 #ifdef __cplusplus
 }

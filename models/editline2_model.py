@@ -67,49 +67,56 @@ class EditLine2Model(torch.nn.Module):
             composed, mask, _ = self.engine().inference(image, line, precision=self.precision)
             return composed, mask
         if mode == "visualize":
-            composed, mask, ex = self.engine().inference(image, line, precision=self.precision,
-                                                         want=("coarse", "fine", "mask_image", "mask_bin"))
-            mb = ex["mask_bin"]
-            visline = image * (1 - line) + torch.ones_like(image) * line
-            return {"mask": mask, "maskim": ex["mask_image"], "visline": visline, "coarse": ex["coarse"],
-                    "composed": ex["fine"] * mb + image * (1 - mb), "gt": data.get("gt", data["image"])}
+            # reference :134-145 -- 'mask' is the BINARISED mask netG inpaints (mask_inpaint), 'composed' is blended
+            # with the SOFT mask exactly like mode='inference'
+            composed, _, ex = self.engine().inference(image, line, precision=self.precision,
+                                                      want=("coarse", "fine", "mask_image", "mask_bin"))
+            return {"mask": ex["mask_bin"], "maskim": ex["mask_image"], "coarse": ex["coarse"], "fine": ex["fine"],
+                    "composed": composed}
         raise ValueError("|mode| is invalid or training-only: %r" % (mode,))
 
-    def inference_stream(self, loader, depth=2, pinned_ring=True):
+    def inference_stream(self, loader, depth=2, pinned_ring=True, gather=None):
         """Pipelined form of ``for data in loader: model(data, mode='inference')`` for throughput serving.
 
-        Yields ``(composed, mask)`` per batch, in order, as PINNED CPU tensors. The host->device copy of batch
-        i+1 and the device->host copy of batch i-1 run on their own CUDA streams while batch i computes
-        (``depth`` device buffers per tensor), so a step costs max(copy, compute) instead of their sum.
-        Batches whose 'image'/'mask' tensors are in pinned memory (DataLoader(pin_memory=True)) overlap fully.
+        Yields ``(composed, mask)`` per batch, in order, as PINNED CPU tensors (views of one packed [B,4,H,W] host
+        buffer). The host->device copy of batch i+1 and the device->host copy of batch i-1 run on their own CUDA
+        streams while batch i computes (``depth`` device buffers per tensor), so a step costs max(copy, compute)
+        instead of their sum. Batches whose 'image'/'mask' tensors are in pinned memory (DataLoader(pin_memory=True))
+        overlap fully.
 
         pinned_ring=True (default): results are views of a ring of ``depth + 2`` pinned buffers, valid until
         ``depth + 1`` further results have been drawn (consume or ``.clone()`` them, as a save-to-disk loop does);
         pinned_ring=False allocates fresh pinned tensors for every batch (a cudaHostAlloc per batch when the host
-        allocator cannot recycle, which costs more than the copy itself)."""
+        allocator cannot recycle, which costs more than the copy itself).
+
+        gather: a ``sketchedit_b200.parallel.OutputGather`` (data-parallel serving, one process per GPU): every batch's
+        packed outputs are written into this rank's slice of the gather buffer and all-gathered over NCCL (async, in
+        place) before this rank's shard is copied to the host; all ranks must feed equal batch sizes."""
         import collections
         eng = self.engine()
+        if gather is not None and gather.depth != depth:
+            raise ValueError("gather ring depth must equal the stream depth (%d)" % depth)
         dev = torch.device("cuda")
         cur = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         slots = [None] * depth
         pending = collections.deque()
-        ring, ring_pos = {}, [0]
+        ring = {}        # (B, H, W) -> [buffers, results handed out so far]
 
         def host_out(B, H, W):
             if not pinned_ring:
-                return torch.empty(B, 3, H, W, pin_memory=True), torch.empty(B, 1, H, W, pin_memory=True)
-            bufs = ring.setdefault((B, H, W), [])
+                return torch.empty(B, 4, H, W, pin_memory=True)
+            entry = ring.setdefault((B, H, W), [[], 0])
+            bufs, count = entry
             if len(bufs) < depth + 2:
-                bufs.append((torch.empty(B, 3, H, W, pin_memory=True), torch.empty(B, 1, H, W, pin_memory=True)))
-                return bufs[-1]
-            ring_pos[0] += 1
-            return bufs[ring_pos[0] % (depth + 2)]
+                bufs.append(torch.empty(B, 4, H, W, pin_memory=True))
+            entry[1] = count + 1
+            return bufs[count % (depth + 2)]       # strict round robin per shape: 0, 1, .., depth+1, 0, 1, ..
 
         def drain_one():
-            comp_h, mask_h, ev = pending.popleft()
+            packed_h, ev = pending.popleft()
             ev.synchronize()
-            return comp_h, mask_h
+            return packed_h[:, :3], packed_h[:, 3:4]
 
         for i, data in enumerate(loader):
             img_h, line_h = data["image"], data["mask"]
@@ -120,7 +127,7 @@ class EditLine2Model(torch.nn.Module):
                     slot["ev_comp"].synchronize()
                     slot["ev_out"].synchronize()
                 new = lambda c: torch.empty(B, c, H, W, device=dev, dtype=torch.float32)
-                slot = {"shape": (B, H, W), "img": new(3), "line": new(1), "comp": new(3), "mask": new(1),
+                slot = {"shape": (B, H, W), "img": new(3), "line": new(1), "packed": None if gather is not None else new(4),
                         "ev_in": torch.cuda.Event(), "ev_comp": torch.cuda.Event(), "ev_out": torch.cuda.Event()}
                 slots[i % depth] = slot
             s_in.wait_event(slot["ev_comp"])           # the previous user of these input buffers has been computed
@@ -130,17 +137,28 @@ class EditLine2Model(torch.nn.Module):
                 slot["ev_in"].record(s_in)
             cur.wait_event(slot["ev_in"])
             cur.wait_event(slot["ev_out"])             # ... and its outputs have left the device buffers
-            eng.inference(slot["img"], slot["line"], precision=self.precision, out=(slot["comp"], slot["mask"]))
-            slot["ev_comp"].record(cur)
-            s_out.wait_event(slot["ev_comp"])
+            if gather is not None:
+                if (B, H, W) != (gather.B,) + tuple(gather.bufs[0].shape[2:]):
+                    raise ValueError("with gather= every batch must be [%d,*,%d,%d]" % ((gather.B,) + tuple(gather.bufs[0].shape[2:])))
+                out = gather.next_slot()               # (waits, on `cur`, for the collective that last used this buffer)
+                eng.inference_packed(slot["img"], slot["line"], precision=self.precision, out=out)
+                k = gather.launch()
+                slot["ev_comp"].record(cur)            # inputs are free again; the outputs follow the collective:
+                with torch.cuda.stream(s_out):
+                    gather.wait(k)                     # s_out waits for the all-gather of this batch
+                    src = gather.bufs[k][gather.rank * B:(gather.rank + 1) * B]
+            else:
+                eng.inference_packed(slot["img"], slot["line"], precision=self.precision, out=slot["packed"])
+                slot["ev_comp"].record(cur)
+                s_out.wait_event(slot["ev_comp"])
+                src = slot["packed"]
             with torch.cuda.stream(s_out):
-                comp_h, mask_h = host_out(B, H, W)
-                comp_h.copy_(slot["comp"], non_blocking=True)
-                mask_h.copy_(slot["mask"], non_blocking=True)
+                packed_h = host_out(B, H, W)
+                packed_h.copy_(src, non_blocking=True)
                 slot["ev_out"].record(s_out)
                 done = torch.cuda.Event()
                 done.record(s_out)
-            pending.append((comp_h, mask_h, done))
+            pending.append((packed_h, done))
             if len(pending) >= depth:
                 yield drain_one()
         while pending:

@@ -50,7 +50,6 @@ class DeepFillC2Generator(BaseNetwork):
         return []
 
     def forward(self, x, x2, mask, mask2, guide=None):
-        if guide is None:
-            import torch
-            guide = torch.ones_like(mask)
-        return self.engine().netG(x.float(), x2.float(), mask.float(), mask2.float(), guide.float(), precision=self.precision)
+        # guide=None (reference :127-130: an all-ones sketch channel) is handled inside the library
+        return self.engine().netG(x.float(), x2.float(), mask.float(), mask2.float(), None if guide is None else guide.float(),
+                                  precision=self.precision)

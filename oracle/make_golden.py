@@ -45,16 +45,24 @@ def build_reference_model(flags):
     return model
 
 
-def load_face(name):
+def load_pair(name, release="face_release"):
     from PIL import Image
-    img = Image.open(os.path.join(REF, "datasets/face_release/images", name)).convert("RGB")
-    edge = Image.open(os.path.join(REF, "datasets/face_release/edges", name)).convert("L").resize(img.size)
+    img = Image.open(os.path.join(REF, "datasets", release, "images", name)).convert("RGB")
+    edge = Image.open(os.path.join(REF, "datasets", release, "edges", name)).convert("L").resize(img.size)
     return np.asarray(img, dtype=np.uint8), np.asarray(edge, dtype=np.uint8)
+
+
+def u8_case(img_u8, edge_u8, keep=()):
+    """reference data/testimage_dataset.py:89-103 preprocessing of a (RGB uint8, L uint8) pair."""
+    image = torch.from_numpy(img_u8).permute(2, 0, 1).float().div(255).sub(0.5).div(0.5)[None]
+    sketch = (torch.from_numpy(edge_u8).float().div(255) > 0).float()[None, None]
+    return dict(inputs=(image, sketch), flags={}, u8=(img_u8, edge_u8), keep=keep)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--only", default=None, help="comma-separated case names (default: all)")
     args = ap.parse_args()
     sys.path.insert(0, ROOT)
     from sketchedit_b200 import synth
@@ -71,10 +79,12 @@ def main():
                                                        joint_train_inp=False)),
     }
     # config 1 of BASELINE.json: a real 256x256 face + sketch from the reference's dataset
-    img_u8, edge_u8 = load_face("602_images_celeb_00033.png")
-    face_img = torch.from_numpy(img_u8).permute(2, 0, 1).float().div(255).sub(0.5).div(0.5)[None]
-    face_sk = (torch.from_numpy(edge_u8).float().div(255) > 0).float()[None, None]
-    cases["face_602_256x256"] = dict(inputs=(face_img, face_sk), flags={}, u8=(img_u8, edge_u8))
+    cases["face_602_256x256"] = u8_case(*load_pair("602_images_celeb_00033.png"), keep=("fine", "tap:netM.conv_mask_17"))
+    # config 4 of BASELINE.json (Places-size contextual attention): the reference's non-square general-scene input,
+    # 408 wide x 512 high -> attention over L = 63 * 50 = 3150 patches. Only the end-to-end tensors are kept (file size).
+    cases["places_11_512x408"] = u8_case(*load_pair("11.png", "general_release"))
+    if args.only:
+        cases = {k: v for k, v in cases.items() if k in args.only.split(",")}
 
     os.makedirs(args.out, exist_ok=True)
     for name, case in cases.items():
@@ -110,9 +120,9 @@ def main():
             out["tap:" + k] = v.numpy()
         if "u8" in case:
             out["image_u8"], out["sketch_u8"] = case["u8"]
-            # keep the big case small: only end-to-end tensors + the mask logits
+            # keep the big cases small: only end-to-end tensors (+ what the case asks for)
             for k in list(out):
-                if (k.startswith("tap:") and k != "tap:netM.conv_mask_17") or k == "coarse":
+                if k not in ("composed", "mask", "image_u8", "sketch_u8") + tuple(case["keep"]):
                     del out[k]
         else:
             out["image"], out["sketch"] = image.numpy(), sketch.numpy()

@@ -28,6 +28,7 @@ SIGNATURES = {
     "se_forward_inference": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                       _c_void_p]),
+    "se_forward_inference_packed": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "se_netM_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                  _c_void_p]),
     "se_netG_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
@@ -39,8 +40,8 @@ SIGNATURES = {
     "se_outputs_to_uint8": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "se_last_launch_count": (_c_int, []),
     "se_workspace_bytes": (ctypes.c_longlong, [_c_void_p]),
-    "se_tc_timing_enable": (_c_int, [_c_int]),
-    "se_tc_time_ms": (_c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_int), ctypes.POINTER(ctypes.c_double)]),
+    "se_timing_enable": (_c_int, [_c_int]),
+    "se_timing_report": (_c_int, [_c_char_p, _c_int]),
 }
 
 _lib = None

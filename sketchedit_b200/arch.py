@@ -111,6 +111,17 @@ def conv_flops_per_image(H, W):
     return total
 
 
+def dead_flops_per_image(H, W):
+    """2*MAC of netM's image decoder conv11-17: computed by the reference but unused by mode='inference'
+    (reference models/editline2_model.py:128-133 drops mask_image), skipped here."""
+    total = 0
+    for l in NET_LAYERS["M"]:
+        if l.name.startswith("conv1") and l.name[4:6] in ("11", "12", "13", "14", "15", "16", "17"):
+            h, w = _out_hw(l.name, H, W)
+            total += 2 * h * w * l.cout * l.cin * l.k * l.k
+    return total
+
+
 def cam_flops_per_image(H, W, c=2 * CNUM, patch=4, stride=2):
     """QK^T + AV of the contextual attention: 4*L*N*d."""
     h, w = H // 4, W // 4

@@ -25,11 +25,56 @@ const char* last_error() { return g_err.c_str(); }
 
 static thread_local int g_launches = 0;
 
-// ------------------------------------------------------------------------------------------ tc timing
-static bool g_tc_timing = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_pool;
-static size_t g_ev_used = 0;
-static double g_tc_flops = 0.0;
+// ------------------------------------------------------------------------------------------ launch timing
+// se_timing_enable(1): every launch of a forward is bracketed by CUDA events on its stream and accounted to a kernel
+// class (kernel + layer shape) together with its ALGORITHMIC work: 2*MAC of the reference op, the MACs
+// this implementation really issues (sub-pixel deconvs: 4/9 of the reference's), and the bytes the op must move (input
+// once, output once, weights once). bench.py runs ONE instrumented pass for the roofline table; the throughput passes
+// run with timing off. Process-wide, guarded by a mutex.
+struct TimedLaunch { cudaEvent_t a, b; int cls; };
+struct ClassAgg { std::string name; int tensor; double flops_alg, flops_exec, bytes_alg; int launches; double ms; };
+static std::mutex g_time_mu;
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_tl;
+static size_t g_tl_used = 0;
+static std::vector<ClassAgg> g_classes;
+static std::map<std::string, int> g_class_idx;
+
+struct LaunchTag {
+  std::string name;
+  int tensor = 0;
+  double flops_alg = 0, flops_exec = 0, bytes_alg = 0;
+  bool set = false;
+};
+
+static int timing_begin(const LaunchTag& t, cudaStream_t st, size_t* slot) {
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  const std::string key = t.set ? t.name : std::string("other");
+  auto it = g_class_idx.find(key);
+  int ci;
+  if (it == g_class_idx.end()) {
+    ci = (int)g_classes.size();
+    g_class_idx[key] = ci;
+    g_classes.push_back(ClassAgg{key, t.tensor, 0, 0, 0, 0, 0});
+  } else ci = it->second;
+  ClassAgg& a = g_classes[ci];
+  a.flops_alg += t.flops_alg; a.flops_exec += t.flops_exec; a.bytes_alg += t.bytes_alg; a.launches += 1;
+  if (g_tl_used == g_tl.size()) {
+    TimedLaunch tl;
+    SE_CUDA_OK(cudaEventCreate(&tl.a));
+    SE_CUDA_OK(cudaEventCreate(&tl.b));
+    g_tl.push_back(tl);
+  }
+  *slot = g_tl_used++;
+  g_tl[*slot].cls = ci;
+  SE_CUDA_OK(cudaEventRecord(g_tl[*slot].a, st));
+  return 0;
+}
+static int timing_end(size_t slot, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  SE_CUDA_OK(cudaEventRecord(g_tl[slot].b, st));
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------ architecture
 struct Spec {
@@ -157,6 +202,13 @@ struct se_model {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   std::vector<void*> owned;              // device allocations of packed weights
+  // one forward at a time per model (the workspace arena is shared by every call); the model lives on ONE device; a call
+  // on another stream than the previous one waits for that stream's work on the arena first
+  std::mutex mu;
+  int device = -1;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
+  cudaEvent_t order_ev = nullptr;
 };
 
 namespace se {
@@ -426,19 +478,30 @@ struct Ctx {
   Arena arena;
   int B;
   int rc = 0;
+  LaunchTag tag_;
+  // label + algorithmic work of the NEXT launch (consumed by CK); see "launch timing" above
+  void tag(const std::string& name, int tensor, double flops_alg, double flops_exec, double bytes_alg) {
+    if (!g_timing || dry) return;
+    tag_.name = name; tag_.tensor = tensor; tag_.flops_alg = flops_alg; tag_.flops_exec = flops_exec; tag_.bytes_alg = bytes_alg; tag_.set = true;
+  }
   int act_dt() const { return prec == SE_PREC_FP32_EXACT ? DT_F32 : DT_BF16; }
   size_t esz() const { return prec == SE_PREC_FP32_EXACT ? 4 : 2; }
   Buf get(size_t bytes) { Buf b; b.bytes = bytes; b.p = arena.alloc(bytes); return b; }
   void put(Buf& b) { if (b.p) arena.release(b.p, b.bytes); b.p = nullptr; }
 };
 
-#define CK(expr)                      \
-  do {                                \
-    if (!c.dry) {                     \
-      int _rc = (expr);               \
-      if (_rc) { c.rc = _rc; return _rc; } \
-      ++g_launches;                   \
-    }                                 \
+#define CK(expr)                                                    \
+  do {                                                              \
+    if (!c.dry) {                                                   \
+      size_t _slot = 0;                                             \
+      const bool _timed = g_timing;                                 \
+      if (_timed) { int _rt = timing_begin(c.tag_, c.stream, &_slot); if (_rt) { c.rc = _rt; return _rt; } } \
+      c.tag_.set = false;                                           \
+      int _rc = (expr);                                             \
+      if (_rc) { c.rc = _rc; return _rc; }                          \
+      if (_timed) { int _rt = timing_end(_slot, c.stream); if (_rt) { c.rc = _rt; return _rt; } } \
+      ++g_launches;                                                 \
+    }                                                               \
   } while (0)
 
 // activation view. c8 == 0: NHWC, channels [0,C) at pixel pitch ld. c8 == 1: [B][ld blocks][H][W][8], the view's
@@ -462,26 +525,8 @@ static Layer* find_ready(se_model* m, char net, const std::string& name) {
   return L;
 }
 
-static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw, double flops) {
-  if (c.prec == SE_PREC_BF16_TC && cw.has_tc) {
-    auto go = [&]() -> int { return cw.use_c8 ? c8_launch(cp, cw.c8, c.stream) : tc_launch(cp, cw.tc, c.stream); };
-    if (g_tc_timing) {
-      if (g_ev_used == g_ev_pool.size()) {
-        cudaEvent_t a, b;
-        SE_CUDA_OK(cudaEventCreate(&a));
-        SE_CUDA_OK(cudaEventCreate(&b));
-        g_ev_pool.push_back({a, b});
-      }
-      auto& ev = g_ev_pool[g_ev_used++];
-      SE_CUDA_OK(cudaEventRecord(ev.first, c.stream));
-      int rc = go();
-      if (rc) return rc;
-      SE_CUDA_OK(cudaEventRecord(ev.second, c.stream));
-      g_tc_flops += flops;
-      return 0;
-    }
-    return go();
-  }
+static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw) {
+  if (c.prec == SE_PREC_BF16_TC && cw.has_tc) return cw.use_c8 ? c8_launch(cp, cw.c8, c.stream) : tc_launch(cp, cw.tc, c.stream);
   ConvParams d = cp;
   d.w = cw.w_direct;
   return direct_launch(d, cw.CoutP, c.prec == SE_PREC_FP32_EXACT, c.stream);
@@ -544,8 +589,20 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     cp.osy = cw.osy; cp.ooy = cw.ooy; cp.osx = cw.osx; cp.oox = cw.oox;
     cp.epi = s.act == 1 ? EPI_GATE_RELU : EPI_GATE_ELU;
     cp.scale = 1.0f; cp.colscale = nullptr;
-    const double flops = 2.0 * c.B * Ho * Wo * (double)s.cout * s.cin * (s.deconv ? 9.0 / 4.0 : (double)s.k * s.k);
-    CK(launch_conv(c, cp, cw, flops));
+    if (g_timing && !c.dry) {
+      // algorithmic work of this launch. A deconv layer is 4 sub-pixel class launches: each gets a quarter of the
+      // reference op's 2*MAC (nearest x2 + 3x3 over the (2Ho x 2Wo) output) and issues 4 taps instead of 9.
+      const double pos = (double)c.B * Ho * Wo, ncls = (double)L.cls.size();
+      const double f_alg = 2.0 * pos * s.cout * s.cin * (s.deconv ? 9.0 : (double)s.k * s.k);
+      const double f_exec = 2.0 * pos * s.cout * s.cin * (s.deconv ? 4.0 : (double)s.k * s.k);
+      const double bytes = ((double)c.B * in.H * in.W * s.cin / ncls + pos * (s.cout / 2) + (double)s.cout * s.cin * s.k * s.k / ncls) * c.esz();
+      const bool tcp = c.prec == SE_PREC_BF16_TC && cw.has_tc;
+      char buf[160];
+      snprintf(buf, sizeof(buf), "%s|%s %d->%d k%d s%d d%d @%dx%d", tcp ? (cw.use_c8 ? "conv_c8_kernel" : "conv_tc_kernel") : "conv_direct_kernel",
+               s.deconv ? "deconv-class" : "conv", s.cin, s.cout, s.k, s.stride, s.rate, Ho * cw.osy, Wo * cw.osx);
+      c.tag(buf, tcp ? 1 : 0, f_alg, f_exec, bytes);
+    }
+    CK(launch_conv(c, cp, cw));
   }
   static const bool dbg = getenv("SE_DEBUG_NAN") != nullptr;
   if (dbg && !c.dry && c.act_dt() == DT_BF16) {
@@ -615,17 +672,29 @@ static std::vector<std::string> with_prefix(const std::string& pfx, std::initial
   return v;
 }
 
+// out_bs / msoft_bs: elements between images of out_nchw / mask_soft (0 = dense); non-zero when they are views into a packed
+// [B,4,H,W] output (se_forward_inference_packed)
 static int run_head(Ctx& c, char net, const std::string& name, const View& in, int mode, const float* img, const float* mask_bin,
-                    const float* mask_soft, float* out_nchw, float* out2, void* out_pack8) {
+                    const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, long long out_bs = 0, long long msoft_bs = 0) {
   Layer* L = find_ready(c.m, net, name);
   SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name + ": " + last_error());
+  {
+    // 12-channel map in (two channel blocks on the C8 path), image / mask planes in, cout (+ blend / pack) planes out
+    const double px = (double)c.B * in.H * in.W;
+    const double bytes = px * ((in.c8 ? 16 : 12) * c.esz() + (img ? 12 : 0) + (mask_bin ? 4 : 0) + (mask_soft ? 4 : 0) + (out_nchw ? 4 * L->spec.cout : 0) +
+                               (out2 ? 4 * (mode == HEAD_MASK ? 1 : L->spec.cout) : 0) + (out_pack8 ? 8 * c.esz() : 0));
+    const double fl = 2.0 * px * 9 * 12 * L->spec.cout;
+    c.tag(std::string(in.c8 == 1 && c.act_dt() == DT_BF16 ? "head_c8_kernel" : "head_kernel") + "|12->" + std::to_string(L->spec.cout) + " k3 + " +
+              (mode == HEAD_MASK ? "sigmoid+threshold" : mode == HEAD_TANH ? "tanh" : mode == HEAD_COARSE ? "tanh+blend+pack8" : "tanh+soft blend"),
+          0, fl, fl, bytes);
+  }
   if (in.c8 == 1 && c.act_dt() == DT_BF16) {
     CK(head_c8(in.p, L->w_head_host.data(), L->b_host.data(), L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
-               out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, c.stream));
+               out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, out_bs, msoft_bs, c.stream));
     return 0;
   }
   CK(head(in.p, c.act_dt(), in.c8, L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
-          out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, c.stream));
+          out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, out_bs, msoft_bs, c.stream));
   return 0;
 }
 
@@ -644,7 +713,9 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
 
   Buf rnorm = c.get((size_t)B * C * 4);
   Buf colm = c.get((size_t)B * L * 4);
+  c.tag("plane_sumsq/rnorm|attention key norm", 0, 0, 0, (double)B * h * w * C * c.esz());
   CK(plane_reduce(f.p, dt, B, h * w, C, f.ld, 0, RED_RNORM, (float*)rnorm.p, c.stream));
+  c.tag("cam_colmask_kernel", 0, 0, 0, (double)B * h * w * 4);
   CK(cam_colmask(mask_s, (float*)colm.p, B, h, w, hs, ws, 0.1f, c.stream));
 
   // ---- keys
@@ -656,6 +727,7 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   Buf kbuf = c.get(kbytes);
   SE_REQUIRE(f.ld == C, "attention input must be dense NHWC");
   SE_REQUIRE(!tc || (C % 32 == 0 && (C % 64 == 0 || C % 64 == 32)), "attention channel count");
+  c.tag("cam_pack_k|attention key operand", 0, 0, 0, (double)B * h * w * C * c.esz() + (double)kbytes);
   CK(cam_pack_k(f.p, dt, (const float*)rnorm.p, kbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, ktc.r64, ktc.r32, c.stream));
 
   // ---- logits S[b, n, l] (fp32, row pitch Lpad), scaled by 10 * m_l in the GEMM epilogue
@@ -678,13 +750,16 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cw.tc = ktc;
     cw.tc.data = kbuf.p;
     cp.w_img_stride = (long long)16 * C * Lpad;
-    CK(launch_conv(c, cp, cw, 2.0 * B * L * (double)L * C * 16));
+    c.tag(tc ? "conv_tc_kernel|attention S=QK^T" : "conv_direct_kernel|attention S=QK^T", tc ? 1 : 0, 2.0 * B * L * (double)L * C * 16,
+          2.0 * B * L * (double)L * C * 16, (double)B * h * w * C * c.esz() + (double)kbytes + (double)B * L * Lpad * 4);
+    CK(launch_conv(c, cp, cw));
   }
   c.put(kbuf);
   c.put(rnorm);
 
   // ---- softmax over keys -> P[b, n, 0..Lpad)
   Buf pbuf = c.get((size_t)B * L * Lpad * c.esz());
+  c.tag("softmax_rows|attention", 0, 0, 0, (double)B * L * Lpad * (4 + c.esz()));
   CK(softmax_rows((const float*)sbuf.p, Lpad, pbuf.p, dt, Lpad, (long long)B * L, L, c.stream));
   if (attn_out) {
     // cam_1 returns [B, L(keys), hs, ws]: transpose of P
@@ -702,6 +777,7 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   vtc.img_bytes = tc_weight_bytes_per_image(vtc);
   const size_t per_pc_bytes = tc ? (size_t)B * vtc.img_bytes : (size_t)B * 4 * Lpad * C * 4;
   Buf vbuf = c.get(4 * per_pc_bytes);
+  c.tag("cam_pack_v|attention value operand", 0, 0, 0, (double)B * h * w * C * c.esz() + 4.0 * per_pc_bytes);
   CK(cam_pack_v(f.p, dt, vbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, vtc.r64, (long long)per_pc_bytes, c.stream));
   for (int pc = 0; pc < 4; ++pc) {
     ConvParams cp;
@@ -722,7 +798,10 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cw.tc = vtc;
     cw.tc.data = (const char*)vbuf.p + pc * per_pc_bytes;
     cp.w_img_stride = (long long)4 * Lpad * C;
-    CK(launch_conv(c, cp, cw, 2.0 * B * (h / 2) * (w / 2) * (double)C * L * 4));
+    c.tag(tc ? "conv_tc_kernel|attention out=fold(PV) class" : "conv_direct_kernel|attention out=fold(PV) class", tc ? 1 : 0,
+          2.0 * B * (h / 2) * (w / 2) * (double)C * L * 4, 2.0 * B * (h / 2) * (w / 2) * (double)C * L * 4,
+          ((double)B * L * Lpad + (double)B * 4 * Lpad * C + (double)B * (h / 2) * (w / 2) * C) * c.esz());
+    CK(launch_conv(c, cp, cw));
   }
   c.put(vbuf);
   c.put(pbuf);
@@ -735,9 +814,10 @@ static const std::initializer_list<const char*> kTrunk9 = {"conv1", "conv2_downs
 
 // MDGenerator.forward: x [B,3,H,W], guide [B,1,H,W] -> mask1 (soft, NCHW), optional x_stage1; also the
 // binarised mask plane (mask1 > 0.5) when mask_bin != nullptr.
-static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, float* mask1, float* x_stage1, float* mask_bin) {
+static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, float* mask1, float* x_stage1, float* mask_bin, long long mask1_bs = 0) {
   const int dt = c.act_dt();
   Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * c.esz());
+  c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
   CK(pack8(x, guide, nullptr, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE, 1.0f, 0, c.stream));
   View x9;
   Buf b9;
@@ -762,7 +842,7 @@ static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, fl
   Buf scratch;
   float* mb = mask_bin;
   if (!mb) { scratch = c.get((size_t)c.B * H * W * 4); mb = (float*)scratch.p; }
-  rc = run_head(c, 'M', "conv_mask_17", v, HEAD_MASK, nullptr, nullptr, nullptr, mask1, mb, nullptr);
+  rc = run_head(c, 'M', "conv_mask_17", v, HEAD_MASK, nullptr, nullptr, nullptr, mask1, mb, nullptr, mask1_bs);
   if (rc) return rc;
   c.put(scratch);
   c.put(b);
@@ -772,11 +852,12 @@ static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, fl
 // DeepFillC2Generator.forward. x, x2 [B,3,H,W]; mask, mask2 planes [B,H,W]; guide [B,H,W] or null (ones).
 // Outputs: x_stage1 (optional), x_stage2 (optional NCHW), composed (optional: fine*soft + img*(1-soft)).
 static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, const float* mask2, const float* guide, int H, int W,
-                    float* x_stage1, float* x_stage2, float* composed, const float* mask_soft, const float* blend_img) {
+                    float* x_stage1, float* x_stage2, float* composed, const float* mask_soft, const float* blend_img,
+                    long long composed_bs = 0, long long msoft_bs = 0) {
+  // guide == nullptr: the reference's guide=None -> an all-ones sketch channel (editline_g.py:127-130), built by pack8
   const int dt = c.act_dt();
   const int* opt = c.m->opt;
   const int h = H / 4, w = W / 4;
-  SE_REQUIRE(guide != nullptr, "guide=None (all-ones sketch) is not supported: pass the sketch tensor");
   const size_t e = c.esz();
 
   // ---- stage 1: coarse encoder + style ("warp-in") encoder -> 192-channel concat -> coarse decoder
@@ -786,6 +867,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   Buf cat1 = c.get((size_t)c.B * h * w * 192 * e);
   {
     Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
+    c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
     CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
     std::vector<std::string> names = with_prefix("", kTrunk9);
     names.push_back("conv10_atrous");
@@ -794,6 +876,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   }
   {
     Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
+    c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
     CK(pack8(x2, guide, mask2, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M,
              opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f, 1, c.stream));
     std::vector<std::string> names = with_prefix("w", kTrunk9);
@@ -803,7 +886,9 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, &v, &b);
     if (rc) return rc;
     Buf pooled = c.get((size_t)c.B * 96 * 4);
+    c.tag("plane_reduce|global style pooling", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
     CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, v.c8, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
+    c.tag("broadcast_channels|pooled style vector -> concat blocks", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
     CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, cat_ld, 96, tc, c.stream));
     c.put(pooled);
     c.put(b);
@@ -815,6 +900,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     int rc = run_chain(c, 'G', with_prefix("conv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}),
                        cat_view(cat1.p), true, cat1, &v16, &b16);
     if (rc) return rc;
+    c.tag("memset|pad pixels of the packed stage-2 input", 0, 0, 0, (double)xnow.bytes);
     CK(fill_zero(xnow.p, xnow.bytes, c.stream));   // zero pad pixels of the packed stage-2 input
     rc = run_head(c, 'G', "conv17", v16, HEAD_COARSE, x, mask, nullptr, x_stage1, nullptr, xnow.p);
     if (rc) return rc;
@@ -836,6 +922,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     if (rc) return rc;
     if (opt[SE_OPT_USE_CAM]) {
       Buf ms = c.get((size_t)c.B * h * w * 4);
+      c.tag("avgpool4_kernel", 0, 0, 0, (double)c.B * H * W * 4);
       CK(avgpool4(mask, (float*)ms.p, c.B, H, W, c.stream));
       Buf camo = c.get((size_t)c.B * h * w * 96 * e);
       rc = run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr, tc);
@@ -855,7 +942,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
                        cat_view(cat2.p), true, cat2, &v16, &b16);
     if (rc) return rc;
     if (composed) {
-      rc = run_head(c, 'G', "allconv17", v16, HEAD_FINE, blend_img, nullptr, mask_soft, composed, x_stage2, nullptr);
+      rc = run_head(c, 'G', "allconv17", v16, HEAD_FINE, blend_img, nullptr, mask_soft, composed, x_stage2, nullptr, composed_bs, msoft_bs);
     } else {
       rc = run_head(c, 'G', "allconv17", v16, HEAD_TANH, nullptr, nullptr, nullptr, x_stage2, nullptr, nullptr);
     }
@@ -870,6 +957,21 @@ template <typename F>
 static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn) {
   SE_REQUIRE(m && m->finalized, "model not finalized");
   SE_REQUIRE(prec >= 0 && prec <= 2, "precision");
+  std::lock_guard<std::mutex> model_lock(m->mu);
+  {
+    int dev = -1;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    if (m->device < 0) m->device = dev;   // model-less operator holder: bound at first use
+    SE_REQUIRE(dev == m->device, "model lives on device " + std::to_string(m->device) + " but the current device is " + std::to_string(dev));
+    if (m->used && m->last_stream != stream) {
+      // the previous forward may still be using the workspace on its own stream: order this one after it
+      if (!m->order_ev) SE_CUDA_OK(cudaEventCreateWithFlags(&m->order_ev, cudaEventDisableTiming));
+      SE_CUDA_OK(cudaEventRecord(m->order_ev, m->last_stream));
+      SE_CUDA_OK(cudaStreamWaitEvent(stream, m->order_ev, 0));
+    }
+    m->last_stream = stream;
+    m->used = true;
+  }
   Ctx c;
   c.m = m; c.stream = stream; c.prec = prec; c.B = B;
   c.dry = true;
@@ -878,7 +980,7 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn) {
   if (rc) return rc;
   const size_t need = c.arena.peak + 4096;
   if (need > m->arena_bytes) {
-    SE_CUDA_OK(cudaStreamSynchronize(stream));
+    SE_CUDA_OK(cudaDeviceSynchronize());   // every stream that ever used the old slab
     if (m->arena) SE_CUDA_OK(cudaFree(m->arena));
     m->arena = nullptr;
     m->arena_bytes = 0;
@@ -924,6 +1026,7 @@ void se_model_destroy(se_model* m) {
   if (!m) return;
   for (void* p : m->owned) cudaFree(p);
   if (m->arena) cudaFree(m->arena);
+  if (m->order_ev) cudaEventDestroy(m->order_ev);
   delete m;
 }
 
@@ -953,6 +1056,7 @@ int se_model_finalize(se_model* m) {
   int ndev = 0;
   SE_CUDA_OK(cudaGetDeviceCount(&ndev));
   SE_REQUIRE(ndev > 0, "no CUDA device: sketchedit_b200 has no CPU fallback");
+  SE_CUDA_OK(cudaGetDevice(&m->device));   // packed weights and the workspace live on the device current now
   // a net may be left out entirely (stand-alone netM / netG modules); a partially set net is an error
   for (char net : {'M', 'G'}) {
     int nset = 0, ntot = 0;
@@ -976,16 +1080,15 @@ int se_model_finalize(se_model* m) {
   return 0;
 }
 
-int se_forward_inference(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision, float* composed,
-                         float* mask, float* coarse, float* fine, float* mask_image, const float* mask_bin_in, float* mask_bin_out,
-                         void* stream) {
+static int forward_inference(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision, float* composed,
+                             float* mask, long long composed_bs, long long mask_bs, float* coarse, float* fine, float* mask_image,
+                             const float* mask_bin_in, float* mask_bin_out, cudaStream_t st) {
   SE_REQUIRE(image && sketch && composed && mask, "null tensor");
   int rc = check_hw(H, W);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   return with_arena(m, precision, B, st, [&](Ctx& c) -> int {
     Buf mb = c.get((size_t)B * H * W * 4);
-    int r = run_netM(c, image, sketch, H, W, mask, mask_image, (float*)mb.p);
+    int r = run_netM(c, image, sketch, H, W, mask, mask_image, (float*)mb.p, mask_bs);
     if (r) return r;
     const float* mbin = (const float*)mb.p;
     if (mask_bin_in) mbin = mask_bin_in;
@@ -993,11 +1096,26 @@ int se_forward_inference(se_model* m, const float* image, const float* sketch, i
       SE_CUDA_OK(cudaMemcpyAsync(mask_bin_out, mbin, (size_t)B * H * W * 4, cudaMemcpyDeviceToDevice, st));
     }
     // generate_fake: netG(inputs, inputs, mask_bin, mask_bin, line)   (editline2_model.py:368)
-    r = run_netG(c, image, image, mbin, mbin, sketch, H, W, coarse, fine, composed, mask, image);
+    r = run_netG(c, image, image, mbin, mbin, sketch, H, W, coarse, fine, composed, mask, image, composed_bs, mask_bs);
     if (r) return r;
     c.put(mb);
     return 0;
   });
+}
+
+int se_forward_inference(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision, float* composed,
+                         float* mask, float* coarse, float* fine, float* mask_image, const float* mask_bin_in, float* mask_bin_out,
+                         void* stream) {
+  return forward_inference(m, image, sketch, B, H, W, precision, composed, mask, 0, 0, coarse, fine, mask_image, mask_bin_in, mask_bin_out,
+                           (cudaStream_t)stream);
+}
+
+int se_forward_inference_packed(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision, float* packed,
+                                void* stream) {
+  SE_REQUIRE(packed != nullptr, "null tensor");
+  const long long bs = 4LL * H * W;   // [B,4,H,W]: composed in channels 0-2, the soft mask in channel 3
+  return forward_inference(m, image, sketch, B, H, W, precision, packed, packed + 3LL * H * W, bs, bs, nullptr, nullptr, nullptr, nullptr, nullptr,
+                           (cudaStream_t)stream);
 }
 
 int se_netM_forward(se_model* m, const float* x, const float* guide, int B, int H, int W, int precision, float* mask1, float* x_stage1,
@@ -1010,7 +1128,7 @@ int se_netM_forward(se_model* m, const float* x, const float* guide, int B, int 
 
 int se_netG_forward(se_model* m, const float* x, const float* x2, const float* mask, const float* mask2, const float* guide, int B, int H,
                     int W, int precision, float* x_stage1, float* x_stage2, void* stream) {
-  SE_REQUIRE(x && x2 && mask && mask2 && x_stage2, "null tensor");
+  SE_REQUIRE(x && x2 && mask && mask2 && x_stage2, "null tensor");   // guide may be NULL: guide=None of the reference
   int rc = check_hw(H, W);
   if (rc) return rc;
   return with_arena(m, precision, B, (cudaStream_t)stream,
@@ -1104,27 +1222,43 @@ int se_outputs_to_uint8(const float* composed, const float* mask, int B, int H, 
 int se_last_launch_count(void) { return se::g_launches; }
 long long se_workspace_bytes(se_model* m) { return m ? (long long)m->arena_bytes : 0; }
 
-int se_tc_timing_enable(int on) {
-  g_tc_timing = on != 0;
-  g_ev_used = 0;
-  g_tc_flops = 0.0;
+int se_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  g_timing = on != 0;
+  g_tl_used = 0;
+  g_classes.clear();
+  g_class_idx.clear();
   return 0;
 }
 
-int se_tc_time_ms(double* ms, int* launches, double* flops) {
-  double total = 0.0;
-  for (size_t i = 0; i < g_ev_used; ++i) {
+// JSON text: {"classes":[{"name","tensor","launches","ms","flops_alg","flops_exec","bytes_alg"},...]} of everything
+// launched since se_timing_enable(1). Synchronises on the recorded events. Returns the length needed (>= cap: truncated).
+int se_timing_report(char* buf, int cap) {
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  for (auto& a : g_classes) a.ms = 0.0;
+  for (size_t i = 0; i < g_tl_used; ++i) {
     float t = 0.0f;
-    SE_CUDA_OK(cudaEventSynchronize(g_ev_pool[i].second));
-    SE_CUDA_OK(cudaEventElapsedTime(&t, g_ev_pool[i].first, g_ev_pool[i].second));
-    total += t;
+    if (cudaEventSynchronize(g_tl[i].b) != cudaSuccess || cudaEventElapsedTime(&t, g_tl[i].a, g_tl[i].b) != cudaSuccess) {
+      set_error("se_timing_report: event query failed");
+      return -1;
+    }
+    g_classes[g_tl[i].cls].ms += t;
   }
-  if (ms) *ms = total;
-  if (launches) *launches = (int)g_ev_used;
-  if (flops) *flops = g_tc_flops;
-  g_ev_used = 0;
-  g_tc_flops = 0.0;
-  return 0;
+  std::string out = "{\"classes\":[";
+  for (size_t i = 0; i < g_classes.size(); ++i) {
+    const ClassAgg& a = g_classes[i];
+    char num[256];
+    snprintf(num, sizeof(num), "\",\"tensor\":%d,\"launches\":%d,\"ms\":%.6f,\"flops_alg\":%.6e,\"flops_exec\":%.6e,\"bytes_alg\":%.6e}", a.tensor, a.launches,
+             a.ms, a.flops_alg, a.flops_exec, a.bytes_alg);
+    out += std::string(i ? "," : "") + "{\"name\":\"" + a.name + num;
+  }
+  out += "]}";
+  if (buf && cap > 0) {
+    const size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int)out.size() + 1;
 }
 
 }  // extern "C"

@@ -49,7 +49,7 @@ __global__ void pack8_kernel(const float* __restrict__ img, const float* __restr
   __align__(16) T v[8];
 #pragma unroll
   for (int c = 0; c < 3; ++c) v[c] = from_f<T>(img[(b * 3 + c) * HW + pix] * a);
-  v[3] = from_f<T>(sketch ? sketch[i] * sketch_scale : 0.0f);
+  v[3] = from_f<T>((sketch ? sketch[i] : 1.0f) * sketch_scale);   // guide=None -> ones (reference editline_g.py:127-130)
   v[4] = from_f<T>(write_mask ? m : 0.0f);
   v[5] = v[6] = v[7] = from_f<T>(0.0f);
   if (sizeof(T) == 2) {
@@ -79,7 +79,9 @@ template <typename T, int COUT>
 __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w /*[9][12][COUT]*/, const float* __restrict__ bias,
                             int B, int H, int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
                             const float* __restrict__ mask_soft, float* __restrict__ out_nchw, float* __restrict__ out2,
-                            T* __restrict__ out_pack8, int no_mask_coarse, int Wp, int padl, int in_c8) {
+                            T* __restrict__ out_pack8, int no_mask_coarse, int Wp, int padl, int in_c8, long long obs, long long msbs) {
+  // obs: elements between images of out_nchw (COUT*HW when dense; 4*HW when it is a view into a packed [B,4,H,W] output);
+  // msbs: likewise for mask_soft
   __shared__ float ws[9 * 12 * COUT + COUT];
   for (int i = threadIdx.x; i < 9 * 12 * COUT; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < COUT) ws[9 * 12 * COUT + threadIdx.x] = bias[threadIdx.x];
@@ -116,7 +118,7 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
   }
   if (mode == HEAD_MASK) {
     const float s = 1.0f / (1.0f + expf(-acc[0]));
-    out_nchw[i] = s;
+    out_nchw[b * obs + pix] = s;
     out2[i] = s > 0.5f ? 1.0f : 0.0f;
     return;
   }
@@ -125,12 +127,12 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
   for (int o = 0; o < COUT; ++o) t3[o] = tanhf(acc[o]);
   if (mode == HEAD_TANH) {
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+    for (int o = 0; o < COUT; ++o) out_nchw[b * obs + o * HW + pix] = t3[o];
   } else if (mode == HEAD_COARSE) {
     const float m = mask_bin[i];
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
-      if (out_nchw) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+      if (out_nchw) out_nchw[b * obs + o * HW + pix] = t3[o];
       const float xin = img[(b * 3 + o) * HW + pix] * (1.0f - m);
       const float v = no_mask_coarse ? t3[o] : (t3[o] * m + xin * (1.0f - m));
       out_pack8[((b * H + yy) * Wp + xx + padl) * 8 + o] = from_f<T>(v);
@@ -138,11 +140,11 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
 #pragma unroll
     for (int o = COUT; o < 8; ++o) out_pack8[((b * H + yy) * Wp + xx + padl) * 8 + o] = from_f<T>(0.0f);
   } else {  // HEAD_FINE
-    const float m = mask_soft[i];
+    const float m = mask_soft[b * msbs + pix];
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
       if (out2) out2[(b * COUT + o) * HW + pix] = t3[o];
-      out_nchw[(b * COUT + o) * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      out_nchw[b * obs + o * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
     }
   }
 }
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
                                                       int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
                                                       const float* __restrict__ mask_soft, float* __restrict__ out_nchw,
                                                       float* __restrict__ out2, __nv_bfloat16* __restrict__ out_pack8, int no_mask_coarse,
-                                                      int Wp, int padl) {
+                                                      int Wp, int padl, long long obs, long long msbs) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long HW = (long long)H * W;
   if (i >= B * HW) return;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
   for (int o = 0; o < COUT; ++o) r[o] = hw.b[o] + (__uint_as_float((uint32_t)acc[o]) + __uint_as_float((uint32_t)(acc[o] >> 32)));
   if (mode == HEAD_MASK) {
     const float sg = 1.0f / (1.0f + expf(-r[0]));
-    out_nchw[i] = sg;
+    out_nchw[b * obs + pix] = sg;
     out2[i] = sg > 0.5f ? 1.0f : 0.0f;
     return;
   }
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
   for (int o = 0; o < COUT; ++o) t3[o] = tanhf(r[o]);
   if (mode == HEAD_TANH) {
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+    for (int o = 0; o < COUT; ++o) out_nchw[b * obs + o * HW + pix] = t3[o];
   } else if (mode == HEAD_COARSE) {
     const float m = mask_bin[i];
     __align__(16) __nv_bfloat16 pk[8];
@@ -219,17 +221,17 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
     for (int o = 0; o < 8; ++o) pk[o] = __float2bfloat16(0.0f);
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
-      if (out_nchw) out_nchw[(b * COUT + o) * HW + pix] = t3[o];
+      if (out_nchw) out_nchw[b * obs + o * HW + pix] = t3[o];
       const float xin = img[(b * 3 + o) * HW + pix] * (1.0f - m);
       pk[o] = __float2bfloat16(no_mask_coarse ? t3[o] : (t3[o] * m + xin * (1.0f - m)));
     }
     *reinterpret_cast<uint4*>(out_pack8 + ((b * H + yy) * Wp + xx + padl) * 8) = *reinterpret_cast<const uint4*>(pk);
   } else {  // HEAD_FINE
-    const float m = mask_soft[i];
+    const float m = mask_soft[b * msbs + pix];
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
       if (out2) out2[(b * COUT + o) * HW + pix] = t3[o];
-      out_nchw[(b * COUT + o) * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      out_nchw[b * obs + o * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
     }
   }
 }
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
 template <int COUT>
 static int head_c8_launch(const void* x, const float* w_host, const float* b_host, int B, int H, int W, int mode, const float* img,
                           const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
-                          int Wp, int padl, cudaStream_t s) {
+                          int Wp, int padl, long long obs, long long msbs, cudaStream_t s) {
   HeadWeights<COUT> hw;
   for (int t = 0; t < 9; ++t)
     for (int p = 0; p < 6; ++p)
@@ -245,29 +247,32 @@ static int head_c8_launch(const void* x, const float* w_host, const float* b_hos
   for (int o = 0; o < COUT; ++o) hw.b[o] = b_host[o];
   const long long n = (long long)B * H * W;
   head_c8_kernel<COUT><<<cdiv(n, 128), 128, 0, s>>>((const __nv_bfloat16*)x, hw, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2,
-                                                    (__nv_bfloat16*)out_pack8, no_mask_coarse, Wp, padl);
+                                                    (__nv_bfloat16*)out_pack8, no_mask_coarse, Wp, padl, obs ? obs : (long long)COUT * H * W,
+                                                    msbs ? msbs : (long long)H * W);
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }
 // w_host / b_host: host copies of the [9][12][cout] weights and the bias (kernel parameters are built from them)
 int head_c8(const void* x, const float* w_host, const float* b_host, int cout, int B, int H, int W, int mode, const float* img,
             const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse, int Wp, int padl,
-            cudaStream_t s) {
+            long long obs, long long msbs, cudaStream_t s) {
   SE_REQUIRE(cout == 1 || cout == 3, "head cout");
-  if (cout == 1) return head_c8_launch<1>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, s);
-  return head_c8_launch<3>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, s);
+  if (cout == 1) return head_c8_launch<1>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, obs, msbs, s);
+  return head_c8_launch<3>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, obs, msbs, s);
 }
 
 int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
-         int Wp, int padl, cudaStream_t s) {
+         int Wp, int padl, long long obs, long long msbs, cudaStream_t s) {
   const long long n = (long long)B * H * W;
   SE_REQUIRE(cout == 1 || cout == 3, "head cout");
+  if (!obs) obs = (long long)cout * H * W;
+  if (!msbs) msbs = (long long)H * W;
   SE_DISPATCH_T(dt, {
     if (cout == 1)
-      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8);
+      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8, obs, msbs);
     else
-      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8);
+      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8, obs, msbs);
   });
   SE_CUDA_OK(cudaGetLastError());
   return 0;

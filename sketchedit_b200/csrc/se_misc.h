@@ -12,10 +12,10 @@ int pack8(const float* img, const float* sketch, const float* mask, void* out, i
           int img_mode, float sketch_scale, int write_mask, cudaStream_t s);
 int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
-         int Wp, int padl, cudaStream_t s);
+         int Wp, int padl, long long out_bstride, long long msoft_bstride, cudaStream_t s);   // strides: elements between images, 0 = dense
 int head_c8(const void* x, const float* w_host, const float* b_host, int cout, int B, int H, int W, int mode, const float* img,
             const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse, int Wp, int padl,
-            cudaStream_t s);
+            long long out_bstride, long long msoft_bstride, cudaStream_t s);
 int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int c8, int mode, float* out, cudaStream_t s);
 int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, int c8, cudaStream_t s);
 int avgpool4(const float* m, float* out, int B, int H, int W, cudaStream_t s);

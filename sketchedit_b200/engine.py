@@ -28,6 +28,19 @@ def _chk_in(t, shape_tail=None, name="tensor"):
     return t.contiguous()
 
 
+def _chk_out(t, shape, name):
+    """Caller-owned output: the kernels write through its pointer, so a silent .contiguous() copy is not an option."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise _lib.SketchEditB200Error("%s must be a contiguous CUDA float32 tensor" % name)
+    if tuple(t.shape) != tuple(shape):
+        raise _lib.SketchEditB200Error("%s must have shape %r (got %r)" % (name, tuple(shape), tuple(t.shape)))
+    return t
+
+
+def _f32(*shape, like):
+    return torch.empty(*shape, device=like.device, dtype=torch.float32)
+
+
 class Engine:
     def __init__(self):
         self.lib = _lib.load()
@@ -79,6 +92,12 @@ class Engine:
             raise _lib.SketchEditB200Error("sketchedit_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         _lib.check(self.lib.se_model_finalize(self.h))
         self.finalized = True
+        self.device = torch.device("cuda", torch.cuda.current_device())   # weights + workspace live here
+
+    def _on_device(self, *tensors):
+        for t in tensors:
+            if t is not None and t.device != self.device:
+                raise _lib.SketchEditB200Error("tensor on %s but this engine was finalized on %s" % (t.device, self.device))
 
     @classmethod
     def from_state_dicts(cls, sd_M, sd_G, **options):
@@ -99,26 +118,38 @@ class Engine:
         image = _chk_in(image, name="image")
         sketch = _chk_in(sketch, name="sketch")
         B, _, H, W = image.shape
-        new = lambda c: torch.empty(B, c, H, W, device=image.device, dtype=torch.float32)
+        new = lambda c: _f32(B, c, H, W, like=image)
         if out is not None:
-            composed, mask = _chk_in(out[0], name="out[0]"), _chk_in(out[1], name="out[1]")
-            if tuple(composed.shape) != (B, 3, H, W) or tuple(mask.shape) != (B, 1, H, W):
-                raise _lib.SketchEditB200Error("out tensors must be [B,3,H,W] and [B,1,H,W]")
+            composed, mask = _chk_out(out[0], (B, 3, H, W), "out[0]"), _chk_out(out[1], (B, 1, H, W), "out[1]")
         else:
             composed, mask = new(3), new(1)
         extra = {k: new(1 if k == "mask_bin" else 3) for k in want}
         mb_in = _chk_in(mask_bin, name="mask_bin") if mask_bin is not None else None
+        self._on_device(image, sketch, composed, mask, mb_in)
         _lib.check(self.lib.se_forward_inference(
             self.h, _ptr(image), _ptr(sketch), B, H, W, _lib.PREC[precision], _ptr(composed), _ptr(mask),
             _ptr(extra.get("coarse")), _ptr(extra.get("fine")), _ptr(extra.get("mask_image")), _ptr(mb_in),
             _ptr(extra.get("mask_bin")), _stream()))
         return composed, mask, extra
 
+    def inference_packed(self, image, sketch, precision="bf16", out=None):
+        """Same forward, ONE packed output [B,4,H,W] (channels 0-2 composed, channel 3 the soft mask) = the layout of the
+        data-parallel output all-gather: ``out`` may be this rank's slice of the gather buffer (parallel.OutputGather)."""
+        image = _chk_in(image, name="image")
+        sketch = _chk_in(sketch, name="sketch")
+        B, _, H, W = image.shape
+        packed = _f32(B, 4, H, W, like=image) if out is None else _chk_out(out, (B, 4, H, W), "out")
+        self._on_device(image, sketch, packed)
+        _lib.check(self.lib.se_forward_inference_packed(self.h, _ptr(image), _ptr(sketch), B, H, W, _lib.PREC[precision], _ptr(packed),
+                                                        _stream()))
+        return packed
+
     def netM(self, x, guide, precision="bf16", want_image=True):
         x, guide = _chk_in(x), _chk_in(guide)
         B, _, H, W = x.shape
-        mask1 = torch.empty(B, 1, H, W, device=x.device)
-        st1 = torch.empty(B, 3, H, W, device=x.device) if want_image else None
+        self._on_device(x, guide)
+        mask1 = _f32(B, 1, H, W, like=x)
+        st1 = _f32(B, 3, H, W, like=x) if want_image else None
         _lib.check(self.lib.se_netM_forward(self.h, _ptr(x), _ptr(guide), B, H, W, _lib.PREC[precision], _ptr(mask1), _ptr(st1),
                                             _stream()))
         return mask1, st1
@@ -127,8 +158,9 @@ class Engine:
         x, x2, mask, mask2 = _chk_in(x), _chk_in(x2), _chk_in(mask), _chk_in(mask2)
         guide = _chk_in(guide) if guide is not None else None
         B, _, H, W = x.shape
-        s1 = torch.empty(B, 3, H, W, device=x.device)
-        s2 = torch.empty(B, 3, H, W, device=x.device)
+        self._on_device(x, x2, mask, mask2, guide)
+        s1 = _f32(B, 3, H, W, like=x)
+        s2 = _f32(B, 3, H, W, like=x)
         _lib.check(self.lib.se_netG_forward(self.h, _ptr(x), _ptr(x2), _ptr(mask), _ptr(mask2), _ptr(guide), B, H, W,
                                             _lib.PREC[precision], _ptr(s1), _ptr(s2), _stream()))
         return s1, s2
@@ -143,7 +175,8 @@ class Engine:
             Ho, Wo = 2 * H, 2 * W
         else:
             Ho, Wo = (H + spec.stride - 1) // spec.stride, (W + spec.stride - 1) // spec.stride
-        y = torch.empty(B, out_channels_after_gate(spec), Ho, Wo, device=x.device)
+        self._on_device(x)
+        y = _f32(B, out_channels_after_gate(spec), Ho, Wo, like=x)
         _lib.check(self.lib.se_gated_conv_forward(self.h, net.encode(), name.encode(), _ptr(x), B, H, W, _lib.PREC[precision],
                                                   _ptr(y), _stream()))
         return y
@@ -160,11 +193,11 @@ def contextual_attention(feat, mask_s, precision="bf16", want_attn=False):
     lib = _lib.load()
     feat, mask_s = _chk_in(feat), _chk_in(mask_s)
     B, C, h, w = feat.shape
-    out = torch.empty_like(feat)
+    out = _f32(*feat.shape, like=feat)
     attn = None
     if want_attn:
         hs, ws = (h - 4) // 2 + 1, (w - 4) // 2 + 1
-        attn = torch.empty(B, hs * ws, hs * ws, device=feat.device)
+        attn = _f32(B, hs * ws, hs * ws, like=feat)
     _lib.check(lib.se_contextual_attention_forward(_ptr(feat), _ptr(mask_s), B, C, h, w, _lib.PREC[precision], _ptr(out), _ptr(attn),
                                                    _stream()))
     return (out, attn) if want_attn else out

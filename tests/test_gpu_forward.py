@@ -81,7 +81,8 @@ def test_fp32_path_matches_reference_golden(name, golden_dir):
     ref_bin = (torch.from_numpy(z["mask"]) > 0.5).float()
     assert int((ex["mask_bin"].cpu() != ref_bin).sum()) == 0
     assert maxdiff(mask.cpu(), torch.from_numpy(z["mask"])) <= 1e-3
-    assert maxdiff(ex["fine"].cpu(), torch.from_numpy(z["fine"])) <= 1e-3
+    if "fine" in z:
+        assert maxdiff(ex["fine"].cpu(), torch.from_numpy(z["fine"])) <= 1e-3
     assert maxdiff(composed.cpu(), torch.from_numpy(z["composed"])) <= 1e-3
 
 

@@ -65,7 +65,11 @@ def test_gated_conv_bf16_tensor_core(net, name, H, W):
     assert maxdiff(y, ref) <= tol, (name, maxdiff(y, ref), tol)
 
 
-@pytest.mark.parametrize("h,w,B", [(16, 16, 2), (12, 20, 1), (32, 32, 1)])
+# (128, 128): Places config, L = 3969 keys; (128, 102): the reference's 408-wide input, L = 63 * 50 = 3150; (64, 64): CelebA, L = 961
+CAM_CASES = [(16, 16, 2), (12, 20, 1), (32, 32, 1), (64, 64, 2), (128, 128, 1), (128, 102, 1)]
+
+
+@pytest.mark.parametrize("h,w,B", CAM_CASES)
 def test_contextual_attention_fp32(h, w, B):
     feat = F.relu(rand_act((B, 96, h, w), seed=h * w))          # pmconv6 output is ReLU-gated: non-negative
     mask = torch.zeros(B, 1, 4 * h, 4 * w)
@@ -78,7 +82,7 @@ def test_contextual_attention_fp32(h, w, B):
     assert maxdiff(out.cpu(), ref) <= 2e-4 * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("h,w,B", [(16, 16, 2), (12, 20, 1), (32, 32, 1)])
+@pytest.mark.parametrize("h,w,B", CAM_CASES)
 def test_contextual_attention_bf16(h, w, B):
     # soft attention (small features) so bf16 logits cannot flip a hard arg-max
     feat = F.relu(rand_act((B, 96, h, w), seed=h * w + 1, scale=0.15))
