@@ -84,8 +84,9 @@ class EditLine2Model(torch.nn.Module):
         instead of their sum. Batches whose 'image'/'mask' tensors are in pinned memory (DataLoader(pin_memory=True))
         overlap fully.
 
-        pinned_ring=True (default): results are views of a ring of ``depth + 2`` pinned buffers, valid until
-        ``depth + 1`` further results have been drawn (consume or ``.clone()`` them, as a save-to-disk loop does);
+        pinned_ring=True (default): results are views of a ring of ``depth + 2`` pinned buffers handed out round robin. The
+        copy of batch i + depth - 1 is already in flight when result i is drawn, so a result stays intact while at most
+        ``depth`` further results are drawn (you may hold the newest ``depth + 1``; consume or ``.clone()`` older ones);
         pinned_ring=False allocates fresh pinned tensors for every batch (a cudaHostAlloc per batch when the host
         allocator cannot recycle, which costs more than the copy itself).
 

@@ -97,6 +97,7 @@ struct EpiParams {
   float scale;
   const float* colscale;
   int Cout, NT;
+  int has_bias;   // 0: the launch has no bias vector (attention GEMMs): no per-column constants are staged in shared memory
   int goff;   // gated epilogues: accumulator column of gate channel 0 (= Cout/2 rounded up to 8; the weight image
               // places feature c at column c and its gate at goff + c, columns in between are zero weights)
 };

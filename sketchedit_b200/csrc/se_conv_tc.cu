@@ -88,7 +88,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // bias (all N tiles) into shared memory; zero when absent
-  const int cst_n = p.n_tiles * p.NT + 32;
+  const int cst_n = (p.e.has_bias ? p.n_tiles * p.NT : 0) + 32;   // attention S has up to 32 N tiles and no bias: nothing to stage
   epi_fill_constants(bias_s, cst_n, p.bias, p.e, threadIdx.x, NUM_THREADS);
   tc_fence_before();
   __syncthreads();
@@ -289,6 +289,7 @@ void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
   e->osy = c.osy; e->ooy = c.ooy; e->osx = c.osx; e->oox = c.oox;
   e->epi = c.epi; e->scale = c.scale; e->colscale = c.colscale;
   e->Cout = c.Cout; e->NT = NT;
+  e->has_bias = c.bias != nullptr ? 1 : 0;
   e->goff = (c.epi == EPI_LINEAR) ? 0 : gated_goff(c.Cout);
 }
 // the fast epilogue addresses the output in 32-bit units of 16 B
@@ -337,7 +338,7 @@ int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_by
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   SE_REQUIRE(stages >= 2, "pipeline needs >= 2 stages");
   p.num_stages = stages;
-  *smem_bytes = 1024 + stages * stage_bytes + (2 * MAX_STAGES + 4) * 8 + 16 + 3 * (p.n_tiles * p.NT + 32) * 4 + 64;
+  *smem_bytes = 1024 + stages * stage_bytes + (2 * MAX_STAGES + 4) * 8 + 16 + 3 * ((c.bias ? p.n_tiles * p.NT : 0) + 32) * 4 + 64;
   *out = p;
   return 0;
 }

@@ -500,7 +500,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& e, const float
         for (int i = 0; i < 16; ++i) {
           float sc = e.scale;
           if (cs != nullptr && i < cnt) sc *= __ldg(cs + cb + i);
-          v[i] = (i < cnt) ? (v[i] + cst[cb + i]) * sc : 0.0f;
+          v[i] = (i < cnt) ? (v[i] + (e.has_bias ? cst[cb + i] : 0.0f)) * sc : 0.0f;
         }
         epi_store16<kFast>(e, img, oy, ox, cb, v, cnt);
       }

@@ -22,7 +22,7 @@ for step in "$@"; do
     env) export "$rest" ;;
     tests)
       if [ -n "$rest" ]; then K=(-k "$rest"); else K=(); fi
-      ( timeout 1500 python -m pytest tests -q -m gpu --timeout 900 "${K[@]}" 2>&1 | tail -30 ) > gpurun_out/pytest_gpu.log 2>&1; cat gpurun_out/pytest_gpu.log ;;
+      timeout 1500 python -m pytest tests -q -m gpu --timeout 900 "${K[@]}" > gpurun_out/pytest_gpu.log 2>&1; tail -${TAIL:-40} gpurun_out/pytest_gpu.log ;;
     smoke) ( timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -5 ) > gpurun_out/smoke.log 2>&1; cat gpurun_out/smoke.log ;;
     bench)
       args=$(echo "$rest" | tr ',' ' '); t=$(tag "bench_$rest")
