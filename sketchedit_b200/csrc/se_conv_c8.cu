@@ -20,6 +20,7 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "se_tc_device.cuh"
@@ -60,7 +61,14 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, bool sw128) 
 // depends on the k-step index (A-offset table index, accumulate flag, last-step test, resident B address) is then a
 // compile-time constant, so the issue sequence is just "constant-bank offset + base -> descriptor -> MMA": the
 // indexed constant loads of the generic form (~100+ cycles each, on the critical path of a 15-18 MMA tile) disappear.
-template <int R64, int R32, int MMAS, int PAIR, int KS1 = 0>
+//
+// NCLS > 1 (2 or 4; KS1 layers only): fused sub-pixel classes of a x2 deconv (C8Group). The persistent loop runs over
+// VIRTUAL tiles v = tile * NCLS + class: the producer loads one (union) halo per real tile; the two MMA issuers take
+// alternate virtual tiles (issuer `me` gets the classes of its parity) and each commits the halo buffer back after its last
+// class of the tile (a_empty counts 2 arrivals); TMEM stages and epilogue groups are indexed by v, so with NCLS = 4 epilogue
+// group g always drains class g. A class selects its resident weight image (cls_bytes apart), its A-offset row
+// aoff[class * C8_CLS_UNITS + unit] (compile-time class index -> constant-bank operands) and its output sub-pixel offset.
+template <int R64, int R32, int MMAS, int PAIR, int KS1 = 0, int NCLS = 1>
 __global__ void __launch_bounds__(TC_NUM_THREADS, 1)
 conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const C8Params p) {
   constexpr bool kPair = PAIR != 0;
@@ -111,7 +119,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < C8_MAX_ABUFS; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], NCLS > 1 ? 2 : 1);   // fused classes: one commit per MMA issuer
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -228,6 +236,64 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t off_wres = halo ? (uint32_t)(p.a_bufs * p.a_bytes) : 0u;
     const uint32_t off_stages = off_wres + (p.resident ? (uint32_t)p.wres_bytes : 0u);
     if (p.resident) mbar_wait(wres_bar, 0, 6);
+    if constexpr (NCLS > 1) {
+      // ------------------------------------------------ fused deconv classes (the launcher guarantees two issuers)
+      constexpr int CSH = NCLS == 4 ? 2 : 1;
+      const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int nv = my_tiles * NCLS;
+      const uint32_t a_lo = ((p.lbo_bytes >> 4) & 0x3FFF) << 16;
+      const uint32_t a_hi = ((p.sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
+      const uint32_t b_hi128 = (1024u >> 4) | (1u << 14) | (2u << 29), b_hi64 = (512u >> 4) | (1u << 14) | (4u << 29);
+      const uint32_t kstep16 = p.kstep_bytes >> 4;
+      for (int v = me; v < nv; v += 2) {
+        const int riter = v >> CSH, cls = v & (NCLS - 1);
+        const int as = v & (acc_stages - 1);
+        const uint32_t accphase = (v >> acc_shift) & 1;
+        long long tw = p.dbg ? clock64() : 0;
+        mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
+        if (p.dbg) t_wtmem += clock64() - tw;
+        const int ab = riter & (p.a_bufs - 1);
+        tw = p.dbg ? clock64() : 0;
+        mbar_wait(&a_full[ab], (riter >> p.a_shift) & 1, 7);
+        if (p.dbg) t_whalo += clock64() - tw;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * acc_stride;
+        const uint32_t sA = smem_base + (uint32_t)ab * p.a_bytes;
+        const uint32_t sB = smem_base + off_wres + (uint32_t)cls * (uint32_t)p.cls_bytes;
+        const uint32_t lead = elect_one() ? 1u : 0u;
+        auto issue_cls = [&](auto CLS) {
+          constexpr int C = decltype(CLS)::value;
+          uint32_t acc = 0u;
+#pragma unroll
+          for (int j = 0; j < R64; ++j) {
+            const uint32_t a0 = (sA + p.aoff[C * C8_CLS_UNITS + j]) >> 4;
+            const uint32_t b0 = (sB + j * b64_bytes) >> 4;
+#pragma unroll
+            for (int k = 0; k < MMAS; ++k) {
+              umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+              acc = 1u;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < R32; ++j) {
+            const uint32_t a0 = (sA + p.aoff[C * C8_CLS_UNITS + R64 + j]) >> 4;
+            const uint32_t b0 = (sB + R64 * b64_bytes + j * b32_bytes) >> 4;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
+              acc = 1u;
+            }
+          }
+        };
+        if (cls == 0) issue_cls(std::integral_constant<int, 0>{});
+        else if (cls == 1) issue_cls(std::integral_constant<int, 1>{});
+        else if (NCLS == 4 && cls == 2) issue_cls(std::integral_constant<int, NCLS == 4 ? 2 : 0>{});
+        else issue_cls(std::integral_constant<int, NCLS == 4 ? 3 : 1>{});
+        if (cls >= NCLS - 2) umma_commit_if(lead, &a_empty[ab]);   // this issuer's last class of the tile
+        umma_commit_if(lead, &tmem_full[as]);
+        __syncwarp();
+      }
+    } else {
     for (int iter = me, tile = (me < n_issuers) ? (int)(blockIdx.x + me * gridDim.x) : total_tiles; tile < total_tiles;
          tile += n_issuers * gridDim.x, iter += n_issuers) {
       const int as = iter & (acc_stages - 1);
@@ -311,6 +377,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (staged && ++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
+    }   // NCLS == 1
     if (p.dbg && lane == 0 && warp == 1) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 7] = t_whalo; }
   } else if (warp >= 4) {
     // ==================================================================== epilogue
@@ -324,8 +391,11 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // come from two unsigned divisions (cheaper than stepping the mixed-radix counter through the skipped tiles)
     const int istep = (epi_split == 1) ? TC_EPI_GROUPS : 1;
     const uint32_t tpi = (uint32_t)(p.tiles_x * p.tiles_y);
-    for (int iter = (epi_split == 1) ? grp : 0, tile = blockIdx.x + iter * gridDim.x; tile < total_tiles;
-         tile += istep * gridDim.x, iter += istep) {
+    // fused classes: `iter` counts VIRTUAL tiles (tile * NCLS + class); the launcher guarantees epi_split == 1 for them
+    constexpr int CSH = NCLS == 4 ? 2 : (NCLS == 2 ? 1 : 0);
+    for (int iter = (epi_split == 1) ? grp : 0, tile = blockIdx.x + (iter >> CSH) * gridDim.x; tile < total_tiles;
+         iter += istep, tile = blockIdx.x + (iter >> CSH) * gridDim.x) {
+      const int cls = iter & (NCLS - 1);
       const uint32_t img_u = (uint32_t)tile / tpi, rem = (uint32_t)tile - img_u * tpi;
       const uint32_t ty_u = rem / (uint32_t)p.tiles_x;
       const int img = (int)img_u, ty = (int)ty_u, tx = (int)(rem - ty_u * (uint32_t)p.tiles_x);
@@ -338,14 +408,15 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_stride;
       const int py = ty * C8_TH + ry, px = tx * C8_TW + rx;
       const bool valid = (py < p.Ho) && (px < p.Wo);
+      // output pixel of this position (sub-pixel classes: osy = osx = 2 and a per-class offset)
+      const int oy = py * p.e.osy + (NCLS > 1 ? p.cls_ooy[cls] : p.e.ooy), ox = px * p.e.osx + (NCLS > 1 ? p.cls_oox[cls] : p.e.oox);
       if (KS1 && p.ecst_nb) {   // (only the single-k-step instantiations carry this code: the launcher sets ecst_nb for them alone)
         // constants as kernel parameters (gated, bf16 block output, 2 or 3 blocks, one group per tile)
-        const int oy = py * p.e.osy + p.e.ooy, ox = px * p.e.osx + p.e.oox;
         const bool elu = (p.e.epi == EPI_GATE_ELU);
         if (p.ecst_nb == 3) { if (elu) tc_epilogue_gated_const<true, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); else tc_epilogue_gated_const<false, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); }
         else { if (elu) tc_epilogue_gated_const<true, 2>(p.e, p.ecst, taddr, img, valid, oy, ox); else tc_epilogue_gated_const<false, 2>(p.e, p.ecst, taddr, img, valid, oy, ox); }
-      } else if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
-      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, py, px, epi_split == 1 ? 0 : grp, epi_split);
+      } else if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
+      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
       tc_fence_before();
       if (kPair) {
         __syncwarp();
@@ -454,6 +525,9 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
 #define C8_PAIR_SPECIALISATIONS(X) X(1, 0, 4) X(1, 1, 4) X(3, 0, 4)
 // structures that occur with a single k-step per tile (resident weights): compile-time k-step index (KS1)
 #define C8_KS1_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(4, 4, 4) X(4, 0, 4)
+// fused sub-pixel classes of the two deconv shapes: 48->48 (one 64-channel unit per tap, all 4 classes resident) and
+// 96->96 (64 + 32 channel units per tap, 2 classes resident: one launch per output-row parity)
+#define C8_GROUP_SPECIALISATIONS(X) X(4, 0, 4, 4) X(4, 4, 4, 2) X(4, 0, 4, 2) X(4, 4, 4, 4)
 static int c8_set_smem_attr(int bytes) {
 #define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   C8_SPECIALISATIONS(X)
@@ -463,6 +537,9 @@ static int c8_set_smem_attr(int bytes) {
 #undef X
 #define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   C8_KS1_SPECIALISATIONS(X)
+#undef X
+#define X(a, b, m, n) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0, 1, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  C8_GROUP_SPECIALISATIONS(X)
 #undef X
   SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<-1, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return 0;
@@ -491,6 +568,16 @@ static int c8_dispatch(const C8Params& p, const CUtensorMap& tmA, const CUtensor
 #undef X
     SE_REQUIRE(false, "no CTA-pair instantiation for this k-step structure");
   }
+  if (p.ncls > 1) {
+#define X(a, b, m, n)                                                                             \
+    if (p.r64 == a && p.r32 == b && p.ncls == n) {                                                 \
+      conv_c8_kernel<a, b, m, 0, 1, n><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p); \
+      return 0;                                                                                   \
+    }
+    C8_GROUP_SPECIALISATIONS(X)
+#undef X
+    SE_REQUIRE(false, "no fused-class instantiation for this k-step structure");
+  }
   static const bool no_ks1 = getenv("SE_C8_NOKS1") != nullptr;   // A/B switch for experiments
   if (p.ksteps == 1 && p.resident && p.mode == C8_HALO && !no_ks1) {
 #define X(a, b, m)                                                                             \
@@ -512,6 +599,57 @@ static int c8_dispatch(const C8Params& p, const CUtensorMap& tmA, const CUtensor
   return 0;
 }
 
+static const int kGroupSmemMax = 222 * 1024;   // fused classes may use (almost) the whole opt-in window: weights of all classes + 2 halos
+static bool c8_group_kernel_exists(int r64, int r32, int ncls) {
+#define X(a, b, m, n) if (r64 == a && r32 == b && ncls == n) return true;
+  C8_GROUP_SPECIALISATIONS(X)
+#undef X
+  return false;
+}
+
+int c8_configure_group(C8Group* G, int ncls, int ntaps, const int8_t (*dy)[8], const int8_t (*dx)[8], const int* ooy, const int* oox, int Ci, int Cout) {
+  static const bool off = getenv("SE_C8_NOGROUP") != nullptr;   // A/B switch for experiments
+  if (off || ncls < 2 || ncls > C8_MAX_CLS || ntaps > 8) return 1;
+  int mn_y = 0, mx_y = 0, mn_x = 0, mx_x = 0;
+  for (int c = 0; c < ncls; ++c)
+    for (int t = 0; t < ntaps; ++t) {
+      mn_y = dy[c][t] < mn_y ? dy[c][t] : mn_y; mx_y = dy[c][t] > mx_y ? dy[c][t] : mx_y;
+      mn_x = dx[c][t] < mn_x ? dx[c][t] : mn_x; mx_x = dx[c][t] > mx_x ? dx[c][t] : mx_x;
+    }
+  C8Layer& L = G->geo;
+  L = C8Layer();
+  TcWeights& w = L.w;
+  w.ntaps = ntaps;
+  w.n64 = Ci / 64;
+  int rem = Ci - 64 * w.n64;
+  if (rem > 32) { ++w.n64; rem = 0; }
+  w.n32 = rem > 0 ? 1 : 0;
+  w.NT = (gated_goff(Cout) + Cout / 2 + 15) / 16 * 16;
+  w.n_tiles = 1;
+  w.img_bytes = 0;
+  w.r64 = ntaps * w.n64;      // resident weights + halo: one k-step issues every MMA of a (tile, class)
+  w.r32 = ntaps * w.n32;
+  if (w.r64 + w.r32 > C8_CLS_UNITS || !c8_group_kernel_exists(w.r64, w.r32, ncls)) return 1;
+  L.mode = C8_HALO;
+  L.resident = true;
+  L.stem = false;
+  L.cb_in = (w.n64 * 64 + w.n32 * 32) / 8;
+  L.HR = C8_TH + (mx_y - mn_y); L.WR = C8_TW + (mx_x - mn_x);
+  L.pad_y0 = -mn_y; L.pad_x0 = -mn_x;
+  L.a_tx_bytes = L.cb_in * L.HR * L.WR * 16;
+  L.a_bytes = (L.a_tx_bytes + 1023) / 1024 * 1024;
+  G->ncls = ncls;
+  G->ntaps = ntaps;
+  G->cls_bytes = ntaps * w.NT * (w.n64 * 128 + w.n32 * 64);
+  for (int c = 0; c < ncls; ++c) {
+    for (int t = 0; t < ntaps; ++t) { G->dy[c][t] = dy[c][t]; G->dx[c][t] = dx[c][t]; }
+    G->ooy[c] = ooy[c]; G->oox[c] = oox[c];
+  }
+  // weights of all classes + two halo buffers + barriers / constants must fit the opt-in window
+  if (1024 + ncls * G->cls_bytes + 2 * L.a_bytes + 4096 > kGroupSmemMax) return 1;
+  return 0;
+}
+
 // may this layer run as CTA pairs? (decided at packing time: the pair-format weight image is built only then)
 bool c8_pair_capable(const C8Layer& L) {
   static const bool off = getenv("SE_C8_NOPAIR") != nullptr;
@@ -521,13 +659,14 @@ bool c8_pair_capable(const C8Layer& L) {
   return half_bytes % 512 == 0 && c8_pair_kernel_exists(w.n64 ? w.r64 : 0, w.n32 ? w.r32 : 0, 4);
 }
 
-int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
+int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, const C8Group* grp) {
+  const C8Layer& L = grp ? grp->geo : L_in;
   const TcWeights& w = L.w;
   SE_REQUIRE(c.in_dt == DT_BF16 && c.in_c8 == 1, "conv_c8 reads bf16 channel-blocked activations");
   SE_REQUIRE(c.stride == 1, "conv_c8 handles stride-1 convolutions");
   SE_REQUIRE((reinterpret_cast<uintptr_t>(c.x) & 127) == 0, "input base must be 128 B aligned");
   SE_REQUIRE(c.ntaps == w.ntaps && c.ntaps <= MAX_TAPS, "tap count mismatch");
-  for (int t = 0; t < c.ntaps; ++t) SE_REQUIRE(c.tap_cb[t] == L.tap_cb[t] && (L.tap_cb[t] == 0 || L.mode == C8_HALO), "per-tap channel blocks need the halo mode");
+  for (int t = 0; t < c.ntaps && !grp; ++t) SE_REQUIRE(c.tap_cb[t] == L.tap_cb[t] && (L.tap_cb[t] == 0 || L.mode == C8_HALO), "per-tap channel blocks need the halo mode");
   SE_REQUIRE(c.Wi * 8 <= (1 << 30) && L.WR * 8 <= 256 && L.HR <= 256 && L.cb_in <= 256, "TMA box limits");
   C8Params p;
   memset(&p, 0, sizeof(p));
@@ -539,12 +678,15 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
   memcpy(p.dx, c.dx, sizeof(p.dx));
   p.n64 = w.n64; p.n32 = w.n32; p.r64 = w.n64 ? w.r64 : 0; p.r32 = w.n32 ? w.r32 : 0; p.NT = w.NT;
   p.ksteps = tc_ksteps(w);
-  p.w = reinterpret_cast<const uint8_t*>(w.data);
+  p.w = reinterpret_cast<const uint8_t*>(grp ? grp->w_all : w.data);
   p.mode = L.mode; p.HR = L.HR; p.WR = L.WR; p.pad_y0 = L.pad_y0; p.pad_x0 = L.pad_x0;
   p.cb_in = L.cb_in; p.x_cb_off = c.x_cb_off;
   p.a_bytes = L.a_bytes; p.a_tx_bytes = L.a_tx_bytes;
   p.resident = L.resident ? 1 : 0;
-  p.wres_bytes = (int)tc_weight_bytes_per_image(w);
+  p.wres_bytes = grp ? grp->ncls * grp->cls_bytes : (int)tc_weight_bytes_per_image(w);
+  p.ncls = grp ? grp->ncls : 1;
+  p.cls_bytes = grp ? grp->cls_bytes : 0;
+  for (int k = 0; k < C8_MAX_CLS; ++k) { p.cls_ooy[k] = grp && k < grp->ncls ? grp->ooy[k] : 0; p.cls_oox[k] = grp && k < grp->ncls ? grp->oox[k] : 0; }
   if (L.stem) { p.lbo_bytes = 16; p.kstep_bytes = 32; p.mmas64 = 3; }
   else { p.lbo_bytes = L.HR * L.WR * 16; p.kstep_bytes = 2 * p.lbo_bytes; p.mmas64 = 4; }
   p.sbo_bytes = L.WR * 16;
@@ -574,13 +716,16 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
     const bool halo = (L.mode == C8_HALO);
     const int n_u64 = c.ntaps * w.n64, n_u32 = c.ntaps * w.n32;
     SE_REQUIRE(n_u64 + n_u32 < C8_MAX_UNITS, "too many K units");
-    for (int u = 0; u < n_u64 + n_u32; ++u) {
-      const bool is64 = u < n_u64;
-      const int t = is64 ? u / w.n64 : u - n_u64;
-      const int cb0 = L.tap_cb[t] + (is64 ? (u - t * w.n64) * 8 : w.n64 * 8);
-      const int oy = halo ? c.dy[t] + L.pad_y0 : 0, ox = halo ? c.dx[t] + L.pad_x0 : 0;
-      p.aoff[u] = (uint32_t)((cb0 * L.HR + oy) * L.WR + ox) * 16u;
-    }
+    SE_REQUIRE(!grp || n_u64 + n_u32 <= C8_CLS_UNITS, "too many K units per class");
+    for (int k = 0; k < (grp ? grp->ncls : 1); ++k)
+      for (int u = 0; u < n_u64 + n_u32; ++u) {
+        const bool is64 = u < n_u64;
+        const int t = is64 ? u / w.n64 : u - n_u64;
+        const int cb0 = L.tap_cb[t] + (is64 ? (u - t * w.n64) * 8 : w.n64 * 8);
+        const int tdy = grp ? grp->dy[k][t] : c.dy[t], tdx = grp ? grp->dx[k][t] : c.dx[t];
+        const int oy = halo ? tdy + L.pad_y0 : 0, ox = halo ? tdx + L.pad_x0 : 0;
+        p.aoff[k * C8_CLS_UNITS + u] = (uint32_t)((cb0 * L.HR + oy) * L.WR + ox) * 16u;
+      }
   }
   SE_REQUIRE(c.epi == EPI_LINEAR || (c.Cout % 2 == 0 && c.out_dt == DT_BF16), "gated epilogue needs even Cout, bf16 out");
   SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
@@ -588,21 +733,23 @@ int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream) {
              "space-to-depth output: gated layer, even size, whole channel blocks");
 
   const int total_tiles = p.N * p.tiles_x * p.tiles_y;
-  const bool pair = L.w_pair != nullptr && total_tiles % 2 == 0;
+  const bool pair = !grp && L.w_pair != nullptr && total_tiles % 2 == 0;
+  const int smem_budget = grp ? kGroupSmemMax - 4096 : kSmemBudget;
   const int b_bytes = pair ? tc_stage_b_bytes(w) / 2 : tc_stage_b_bytes(w);   // per CTA
   const int stage_bytes = (L.mode == C8_HALO ? 0 : L.a_bytes) + (L.resident ? 0 : b_bytes);
   int fixed = (L.resident ? p.wres_bytes : 0);
   p.a_bufs = 2;
   if (L.mode == C8_HALO) {
-    if (fixed + 2 * L.a_bytes + 3 * stage_bytes > kSmemBudget) p.a_bufs = 1;   // measured: 2 halo buffers + 3 weight stages beats 1 + 4
+    if (fixed + 2 * L.a_bytes + 3 * stage_bytes > smem_budget) p.a_bufs = 1;   // measured: 2 halo buffers + 3 weight stages beats 1 + 4
     // nothing streamed: a tile is short (700-2000 cycles of MMAs) against a TMA round trip of ~1500 cycles, so two
     // halo buffers leave the tensor pipe waiting for loads; ring as deep as shared memory allows (power of two)
     if (stage_bytes == 0)
-      while (p.a_bufs < C8_MAX_ABUFS && fixed + 2 * p.a_bufs * L.a_bytes <= kSmemBudget) p.a_bufs *= 2;
+      while (p.a_bufs < C8_MAX_ABUFS && fixed + 2 * p.a_bufs * L.a_bytes <= smem_budget) p.a_bufs *= 2;
     fixed += p.a_bufs * L.a_bytes;
   }
   for (p.a_shift = 0; (1 << p.a_shift) < p.a_bufs; ++p.a_shift) {}
-  int stages = stage_bytes ? (kSmemBudget - fixed) / stage_bytes : 1;
+  SE_REQUIRE(!grp || (p.a_bufs >= 2 && w.NT <= 128 && p.ksteps == 1), "fused classes need two halo buffers, <= 128 accumulator columns and a single k-step");
+  int stages = stage_bytes ? (smem_budget - fixed) / stage_bytes : 1;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   { const char* cap = getenv("SE_C8_STAGES"); if (cap && atoi(cap) >= 2 && atoi(cap) < stages) stages = atoi(cap); }   // experiments
   SE_REQUIRE(stages >= (stage_bytes ? 2 : 1), "shared memory plan does not fit");

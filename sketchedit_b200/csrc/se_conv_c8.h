@@ -23,6 +23,22 @@ struct C8Layer {
   const void* w_pair = nullptr;   // CTA-pair format of the stage images (each stage = [rows 0..NT/2) | rows NT/2..NT)), or null
 };
 
+// Sub-pixel classes of one x2 deconv layer fused into ONE launch ("virtual tiles" = tile x class): the union halo of the
+// classes' 2x2 windows is loaded once per tile, the resident weights of all classes sit in shared memory back to back,
+// every (tile, class) gets its own TMEM stage / epilogue group, and the classes' interleaved output pixels are written
+// from one SM within microseconds of each other (whole sectors reach DRAM instead of 16 B slivers per launch).
+constexpr int C8_MAX_CLS = 4;
+constexpr int C8_CLS_UNITS = 16;   // aoff[] stride per class
+struct C8Group {
+  C8Layer geo;                    // union-halo geometry; geo.w = the per-class stage structure (identical for all classes)
+  int ncls = 0;
+  int ntaps = 0;
+  int8_t dy[C8_MAX_CLS][8], dx[C8_MAX_CLS][8];
+  int ooy[C8_MAX_CLS], oox[C8_MAX_CLS];
+  int cls_bytes = 0;              // resident weight image of one class
+  const void* w_all = nullptr;    // device: ncls class images back to back
+};
+
 struct C8Params {
   int N, Ho, Wo;
   int tiles_x, tiles_y;
@@ -43,6 +59,8 @@ struct C8Params {
   // constant-bank operands of the FMAs (no shared-memory loads in the epilogue). ecst_nb = 8-column blocks, 0 = unused
   int ecst_nb;
   float ecst[3][24];
+  int ncls, cls_bytes;            // fused deconv classes (C8Group): classes per tile, bytes between their weight images
+  int cls_ooy[C8_MAX_CLS], cls_oox[C8_MAX_CLS];
   unsigned long long* dbg;
 };
 
@@ -54,6 +72,8 @@ inline uint32_t c8_pair_image_offset(const TcWeights& w, bool is64, int j, int n
   const uint32_t half_bytes = (uint32_t)NTh * (w.r64 * 128 + w.r32 * 64);
   return (uint32_t)(n / NTh) * half_bytes + tc_b_image_offset(NTh, w.n64 ? w.r64 : 0, is64, j, n % NTh, k);
 }
-int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream);
+int c8_launch(const ConvParams& c, const C8Layer& L, cudaStream_t stream, const C8Group* grp = nullptr);
+// geometry of a fused-class launch; returns non-zero (no error text) when the classes do not fit in shared memory
+int c8_configure_group(C8Group* G, int ncls, int ntaps, const int8_t (*dy)[8], const int8_t (*dx)[8], const int* ooy, const int* oox, int Ci, int Cout);
 
 }  // namespace se

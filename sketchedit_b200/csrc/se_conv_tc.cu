@@ -219,8 +219,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
       const int py = ty * TILE_H + ry, px = tx * TILE_W + rx;
       const bool valid = (py < p.Ho) && (px < p.Wo);
-      if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, nt, valid, py, px, grp);
-      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, nt, valid, py, px, grp);
+      const int oy = py * p.e.osy + p.e.ooy, ox = px * p.e.osx + p.e.oox;
+      if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, nt, valid, oy, ox, grp);
+      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, nt, valid, oy, ox, grp);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }

@@ -186,6 +186,7 @@ struct Layer {
   bool set = false;
   std::vector<float> w_host, b_host;
   std::vector<ClassW> cls;
+  std::vector<C8Group> groups; // deconv layers on the tensor-core path: sub-pixel classes fused per launch (se_conv_c8.h)
   float* bias = nullptr;       // device [cout]
   float* w_head = nullptr;     // device [9][12][cout] (heads)
   std::vector<float> w_head_host;   // same, host copy (kernel-parameter weights of the channel-blocked head kernel)
@@ -411,6 +412,36 @@ static int pack_layer(se_model* m, Layer& L) {
     rc = pack_class(m, L, taps, cw);
     if (rc) return rc;
   }
+  // fuse the classes into as few launches as shared memory allows: all four (48->48), else one launch per output-row
+  // parity (96->96: classes {0,1} and {2,3}); the per-class launches stay available as the fallback
+  if (L.cls[0].has_tc && L.cls[0].use_c8 && L.cls[0].c8.resident && L.cls[0].c8.mode == C8_HALO) {
+    for (int per : {4, 2}) {
+      std::vector<C8Group> gs;
+      bool ok = true;
+      for (int g0 = 0; g0 < 4 && ok; g0 += per) {
+        int8_t dy[C8_MAX_CLS][8], dx[C8_MAX_CLS][8];
+        int ooy[C8_MAX_CLS], oox[C8_MAX_CLS];
+        for (int k = 0; k < per; ++k) {
+          const ClassW& cw = L.cls[g0 + k];
+          for (int t = 0; t < cw.ntaps; ++t) { dy[k][t] = cw.dy[t]; dx[k][t] = cw.dx[t]; }
+          ooy[k] = cw.ooy; oox[k] = cw.oox;
+        }
+        C8Group G;
+        if (c8_configure_group(&G, per, L.cls[0].ntaps, dy, dx, ooy, oox, L.Ci, s.cout)) { ok = false; break; }
+        const C8Layer& c0 = L.cls[g0].c8;
+        ok = (G.geo.w.r64 == c0.w.r64 && G.geo.w.r32 == c0.w.r32 && G.geo.w.NT == c0.w.NT && G.cls_bytes == (int)tc_weight_bytes_per_image(c0.w));
+        if (!ok) break;
+        void* d = nullptr;
+        SE_CUDA_OK(cudaMalloc(&d, (size_t)per * G.cls_bytes));
+        m->owned.push_back(d);
+        for (int k = 0; k < per; ++k)
+          SE_CUDA_OK(cudaMemcpy((char*)d + (size_t)k * G.cls_bytes, L.cls[g0 + k].c8.w.data, G.cls_bytes, cudaMemcpyDeviceToDevice));
+        G.w_all = d;
+        gs.push_back(G);
+      }
+      if (ok) { L.groups = gs; break; }
+    }
+  }
   return 0;
 }
 
@@ -555,7 +586,11 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
   const Spec& s = L.spec;
   const int Ho = s.deconv ? in.H : (in.H + s.stride - 1) / s.stride;   // position grid
   const int Wo = s.deconv ? in.W : (in.W + s.stride - 1) / s.stride;
-  for (auto& cw : L.cls) {
+  const bool fused = c.prec == SE_PREC_BF16_TC && !L.groups.empty() && in.c8 == 1;
+  const int n_launch = fused ? (int)L.groups.size() : (int)L.cls.size();
+  for (int li = 0; li < n_launch; ++li) {
+    const C8Group* grp = fused ? &L.groups[li] : nullptr;
+    ClassW& cw = L.cls[fused ? li * grp->ncls : li];
     ConvParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.x = in.p; cp.in_dt = c.act_dt();
@@ -592,17 +627,20 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     if (g_timing && !c.dry) {
       // algorithmic work of this launch. A deconv layer is 4 sub-pixel class launches: each gets a quarter of the
       // reference op's 2*MAC (nearest x2 + 3x3 over the (2Ho x 2Wo) output) and issues 4 taps instead of 9.
-      const double pos = (double)c.B * Ho * Wo, ncls = (double)L.cls.size();
+      // (a fused launch carries `gc` classes)
+      const double gc = grp ? grp->ncls : 1.0;
+      const double pos = (double)c.B * Ho * Wo * gc, ncls = (double)L.cls.size() / gc;
       const double f_alg = 2.0 * pos * s.cout * s.cin * (s.deconv ? 9.0 : (double)s.k * s.k);
       const double f_exec = 2.0 * pos * s.cout * s.cin * (s.deconv ? 4.0 : (double)s.k * s.k);
       const double bytes = ((double)c.B * in.H * in.W * s.cin / ncls + pos * (s.cout / 2) + (double)s.cout * s.cin * s.k * s.k / ncls) * c.esz();
       const bool tcp = c.prec == SE_PREC_BF16_TC && cw.has_tc;
       char buf[160];
       snprintf(buf, sizeof(buf), "%s|%s %d->%d k%d s%d d%d @%dx%d", tcp ? (cw.use_c8 ? "conv_c8_kernel" : "conv_tc_kernel") : "conv_direct_kernel",
-               s.deconv ? "deconv-class" : "conv", s.cin, s.cout, s.k, s.stride, s.rate, Ho * cw.osy, Wo * cw.osx);
+               s.deconv ? (grp ? (grp->ncls == 4 ? "deconv (4 classes fused)" : "deconv (2 classes fused)") : "deconv-class") : "conv", s.cin, s.cout, s.k, s.stride, s.rate, Ho * cw.osy, Wo * cw.osx);
       c.tag(buf, tcp ? 1 : 0, f_alg, f_exec, bytes);
     }
-    CK(launch_conv(c, cp, cw));
+    if (grp) CK(c8_launch(cp, cw.c8, c.stream, grp));
+    else CK(launch_conv(c, cp, cw));
   }
   static const bool dbg = getenv("SE_DEBUG_NAN") != nullptr;
   if (dbg && !c.dry && c.act_dt() == DT_BF16) {

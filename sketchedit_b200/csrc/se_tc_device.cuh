@@ -481,10 +481,10 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
 //   linear: out[c] = (acc[c] + b[c]) * scale * colscale[img][c]
 // The 16-column chunks of a tile are dealt round-robin to `nsplit` warp groups (this one is `grp`); nsplit == 1 means
 // this group drains the whole tile (the groups then alternate tiles).
+// (oy, ox): output pixel of this thread's position (the caller applies the output stride / sub-pixel offset).
 template <bool kFast>
 __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& e, const float* cst, int cst_n, uint32_t taddr, int img, int nt, bool valid,
-                                                 int py, int px, int grp, int nsplit = TC_EPI_GROUPS) {
-  const int oy = py * e.osy + e.ooy, ox = px * e.osx + e.oox;
+                                                 int oy, int ox, int grp, int nsplit = TC_EPI_GROUPS) {
   if (e.epi == EPI_LINEAR) {
     const int n0 = nt * e.NT;
     const float* cs = e.colscale ? e.colscale + (size_t)img * e.Cout : nullptr;
