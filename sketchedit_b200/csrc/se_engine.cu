@@ -14,6 +14,7 @@
 #include "se_common.cuh"
 #include "se_conv_direct.h"
 #include "se_conv_c8.h"
+#include "se_cam.h"
 #include "se_conv_tc.h"
 #include "se_misc.h"
 
@@ -740,6 +741,25 @@ static int run_head(Ctx& c, char net, const std::string& name, const View& in, i
 // cam_1 + cam_2 (reference splitcam.py:57-108,147-174) on an NHWC feature map f [B,h,w,C]:
 //   S = Q K^T  as a stride-2, 4x4-tap "convolution" of f with per-image kernels K   (utils.py:72-99)
 //   A = softmax_l(10 * S * m_l),  out = fold_sum(A V) as four sub-pixel 2x2 convolutions over A
+// bf16 tensor-core path (se_cam.cu): f is the space-to-depth channel-blocked map, out is channel-blocked [B][12][h][w][8]
+static int run_cam_tc(Ctx& c, const View& f, const float* mask_s, void* out, float* attn_out) {
+  SE_REQUIRE(f.c8 == 2 && f.C == 96, "tensor-core attention reads a 96-channel space-to-depth channel-blocked map");
+  CamPlan pl;
+  int rc = cam_plan(c.B, f.H, f.W, &pl);
+  if (rc) return rc;
+  Buf fn = c.get(pl.fn_bytes), cs = c.get(pl.cs_bytes), P = c.get(pl.p_bytes);
+  if (g_timing && !c.dry) {
+    const double L = (double)pl.hs * pl.ws;
+    const double fl = 4.0 * c.B * L * L * 96 * 16;   // QK^T + PV; the statistics sweep repeats QK^T: executed = 1.5x
+    c.tag("cam_s_kernel + cam_pv_kernel (+ norm, colscale)|contextual attention", 1, fl, 1.5 * fl,
+          (double)c.B * f.H * f.W * 96 * 2 * 2 + 2.0 * (double)pl.p_bytes);
+  }
+  CK(cam_forward_tc(f.p, mask_s, out, pl, fn.p, (float*)cs.p, P.p, attn_out, c.stream));
+  if (!c.dry) g_launches += 3;   // four kernels behind one call
+  c.put(P); c.put(cs); c.put(fn);
+  return 0;
+}
+
 static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int out_ld, float* attn_out /*fp32 [B,L,N] or null*/, int out_c8 = 0) {
   SE_REQUIRE(f.c8 == 0, "attention reads an NHWC feature map");
   const int B = c.B, h = f.H, w = f.W, C = f.C;
@@ -956,14 +976,14 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     View pm;
     Buf pmb;
     int rc = run_chain(c, 'G', with_prefix("pm", {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}),
-                       stem_view(c, xnow.p, H, W), true, xnow, &pm, &pmb, nullptr, 0, 0, opt[SE_OPT_USE_CAM] ? 0 : -1);
+                       stem_view(c, xnow.p, H, W), true, xnow, &pm, &pmb, nullptr, 0, 0, opt[SE_OPT_USE_CAM] ? (tc ? 2 : 0) : -1);   // the layout the attention reads
     if (rc) return rc;
     if (opt[SE_OPT_USE_CAM]) {
       Buf ms = c.get((size_t)c.B * h * w * 4);
       c.tag("avgpool4_kernel", 0, 0, 0, (double)c.B * H * W * 4);
       CK(avgpool4(mask, (float*)ms.p, c.B, H, W, c.stream));
       Buf camo = c.get((size_t)c.B * h * w * 96 * e);
-      rc = run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr, tc);
+      rc = tc ? run_cam_tc(c, pm, (const float*)ms.p, camo.p, nullptr) : run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr, 0);
       if (rc) return rc;
       c.put(ms);
       c.put(pmb);
@@ -1240,8 +1260,20 @@ int se_contextual_attention_forward(const float* feat, const float* mask_s, int 
   return with_arena(holder, precision, B, st, [&](Ctx& c) -> int {
     const int dt = c.act_dt();
     Buf in = c.get((size_t)B * h * w * C * c.esz());
-    CK(nchw_to_nhwc(feat, in.p, dt, B, C, h * w, C, 0, st));
     Buf o = c.get((size_t)B * h * w * C * c.esz());
+    if (precision == SE_PREC_BF16_TC && C == 96 && h % 2 == 0 && w % 2 == 0) {
+      // the layouts netG uses on the tensor-core path: space-to-depth channel-blocked in, channel-blocked out
+      CK(nchw_to_c8_s2d(feat, in.p, B, C, h, w, st));
+      View fv = c8view(in.p, h, w, C, 4 * (C / 8), 0);
+      fv.c8 = 2;
+      int r = run_cam_tc(c, fv, mask_s, o.p, attn);
+      if (r) return r;
+      CK(c8_to_nchw(o.p, out, B, C, h * w, st));
+      c.put(o);
+      c.put(in);
+      return 0;
+    }
+    CK(nchw_to_nhwc(feat, in.p, dt, B, C, h * w, C, 0, st));
     int r = run_cam(c, nhwc(in.p, h, w, C, C), mask_s, o.p, C, attn);
     if (r) return r;
     CK(nhwc_to_nchw(o.p, dt, out, B, C, h * w, C, 0, st));

@@ -864,6 +864,24 @@ int nchw_to_c8_s2d(const float* x, void* y, int B, int C, int H, int W, cudaStre
   return 0;
 }
 
+// C8 bf16 [B][C/8][HW][8] -> NCHW fp32 (C % 8 == 0)
+__global__ void c8_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int HW, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i % HW;
+  long long r = i / HW;
+  const int c = (int)(r % C);
+  const long long b = r / C;
+  y[i] = __bfloat162float(x[((b * (C / 8) + (c >> 3)) * HW + p) * 8 + (c & 7)]);
+}
+int c8_to_nchw(const void* x, float* y, int B, int C, int HW, cudaStream_t s) {
+  SE_REQUIRE(C % 8 == 0, "C8 -> NCHW needs whole channel blocks");
+  const long long total = (long long)B * C * HW;
+  c8_to_nchw_kernel<<<cdiv(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, y, C, HW, total);
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s) {
   const long long total = (long long)B * C * HW;
   SE_DISPATCH_T(dt, (nchw_to_nhwc_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, (T*)y, C, HW, ldo, choff, total)));

@@ -28,6 +28,7 @@ int softmax_rows(const float* S, int lds, void* P, int dt, int ldp, long long ro
 int nchw_to_stem8(const float* x, void* y, int dt, int B, int cin, int H, int W, int Wp, int padl, cudaStream_t s);
 int nchw_to_c8_s2d(const float* x, void* y, int B, int C, int H, int W, cudaStream_t s);
 int nchw_to_c8(const float* x, void* y, int B, int C, int HW, cudaStream_t s);
+int c8_to_nchw(const void* x, float* y, int B, int C, int HW, cudaStream_t s);
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s);
 int nhwc_to_nchw(const void* x, int dt, float* y, int B, int C, int HW, int ldx, int choff, cudaStream_t s);
 int to_uint8(const float* comp, const float* mask, unsigned char* bgr, unsigned char* mk, int B, int H, int W, cudaStream_t s);
