@@ -17,11 +17,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug traps instead of hanging the GPU box.
+// Bounded spin: a protocol bug traps after ~2 s of wall time (%globaltimer) instead of hanging the GPU box.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity, const char* what) {
+  printf("sketchedit_b200: %s timeout tag=%d block=%d thread=%d parity=%u\n", what, tag, blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -30,16 +40,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
+    if ((it & 255u) == 255u) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity, "mbarrier");
+    }
   }
-  printf("se_conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-  __trap();
 }
 
 // same, acquiring at cluster scope: the barrier is signalled by threads of the peer CTA (CTA pairs)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
@@ -48,9 +62,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
+    if ((it & 255u) == 255u) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity, "cluster mbarrier");
+    }
   }
-  printf("se_conv_c8: cluster mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-  __trap();
 }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {

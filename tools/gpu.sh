@@ -9,6 +9,8 @@
 #   launches[:ARGS]     ncu launch list (gpu__time_duration) of bench.py --steps 1 ARGS   -> gpurun_out/launches_<ARGS>.csv
 #   traffic:REGEX[:ARGS]  dram bytes + duration per launch of kernels matching REGEX       -> gpurun_out/traffic_<..>.csv
 #   full:REGEX[:ARGS]   ncu --set full --import-source on of kernels matching REGEX (-c 3) -> gpurun_out/full_<..>.ncu-rep
+#   all[:ARGS]          light ncu capture (speed-of-light, memory, tensor pipe, DRAM bytes) of EVERY launch of one forward
+#                                                                    -> gpurun_out/all_<ARGS>.ncu-rep (tools/ncu_summary.py)
 #   probe[:CASES]       SE_TC_DEBUG role timers of single layers (tools/tc_probe.py)
 #   env:K=V             export K=V for the following steps
 #
@@ -44,8 +46,14 @@ for step in "$@"; do
       wc -l gpurun_out/$t.csv ;;
     full)
       rx=${rest%%:*}; a=""; [ "$rest" != "$rx" ] && a=$(echo "${rest#*:}" | tr ',' ' '); t=$(tag "full_${rx}_$a")
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:$rx -s ${SKIP:-60} -c ${COUNT:-3} -o gpurun_out/$t -f \
+      timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base ${NCU_BASE:-function} -k "regex:$rx" -s ${SKIP:-60} -c ${COUNT:-3} -o gpurun_out/$t -f \
         python bench.py --steps 1 --warmup 3 --no-latency $a > gpurun_out/$t.log 2>&1
+      ls -la gpurun_out/$t.ncu-rep ;;
+    all)
+      args=$(echo "$rest" | tr ',' ' '); t=$(tag "all_$rest")
+      timeout 1500 ncu --section SpeedOfLight --section LaunchStats --section MemoryWorkloadAnalysis --section Occupancy \
+        --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
+        --clock-control none -s ${SKIP:-170} -c ${COUNT:-90} -o gpurun_out/$t -f python bench.py --steps 1 --warmup 3 --no-latency $args > gpurun_out/$t.log 2>&1
       ls -la gpurun_out/$t.ncu-rep ;;
     probe)
       ( SE_TC_DEBUG=1 SE_PROBE_CASES=$rest PB=${PB:-32} timeout 300 python tools/tc_probe.py 2>&1 | grep -E "^==|^\[tc\]|^\[c8\]" ) > gpurun_out/probe.log 2>&1
