@@ -207,6 +207,13 @@ struct se_model {
   // one forward at a time per model (the workspace arena is shared by every call); the model lives on ONE device; a call
   // on another stream than the previous one waits for that stream's work on the arena first
   std::mutex mu;
+  // whole-forward CUDA graphs, one per call signature (entry point, shape, precision, options, every pointer argument): the
+  // ~85 launches of a forward (each with its tensor-map encodes) become one cudaGraphLaunch. A signature is captured the
+  // second time it is seen (one-off calls stay eager); entries die with the arena they were captured on.
+  struct GraphEntry { std::vector<uintptr_t> key; cudaGraphExec_t exec = nullptr; void* arena = nullptr; int launches = 0; unsigned long long tick = 0; };
+  std::vector<GraphEntry> graphs;
+  std::map<std::vector<uintptr_t>, int> seen;
+  unsigned long long tick = 0;
   int device = -1;
   cudaStream_t last_stream = nullptr;
   bool used = false;
@@ -1011,8 +1018,11 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
 }
 
 // run `fn` twice: dry (arena peak) then for real
+static const bool g_graphs_on = getenv("SE_NO_GRAPHS") == nullptr;
+constexpr size_t kMaxGraphs = 16;
+
 template <typename F>
-static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn) {
+static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, std::vector<uintptr_t> key = {}) {
   SE_REQUIRE(m && m->finalized, "model not finalized");
   SE_REQUIRE(prec >= 0 && prec <= 2, "precision");
   std::lock_guard<std::mutex> model_lock(m->mu);
@@ -1030,6 +1040,20 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn) {
     m->last_stream = stream;
     m->used = true;
   }
+  // ---- replay a captured forward
+  const bool graphable = g_graphs_on && !g_timing && !key.empty() && getenv("SE_TC_DEBUG") == nullptr && getenv("SE_DEBUG_NAN") == nullptr;
+  if (graphable) {
+    for (int k = 0; k < 8; ++k) key.push_back((uintptr_t)m->opt[k]);
+    key.push_back((uintptr_t)prec);
+    key.push_back((uintptr_t)B);
+    for (auto& g : m->graphs)
+      if (g.exec && g.arena == m->arena && g.key == key) {
+        SE_CUDA_OK(cudaGraphLaunch(g.exec, stream));
+        g.tick = ++m->tick;
+        g_launches = g.launches;
+        return 0;
+      }
+  }
   Ctx c;
   c.m = m; c.stream = stream; c.prec = prec; c.B = B;
   c.dry = true;
@@ -1039,6 +1063,8 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn) {
   const size_t need = c.arena.peak + 4096;
   if (need > m->arena_bytes) {
     SE_CUDA_OK(cudaDeviceSynchronize());   // every stream that ever used the old slab
+    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);   // captured on the old slab
+    m->graphs.clear();
     if (m->arena) SE_CUDA_OK(cudaFree(m->arena));
     m->arena = nullptr;
     m->arena_bytes = 0;
@@ -1048,6 +1074,36 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn) {
   c.dry = false;
   c.arena.reset((char*)m->arena);
   g_launches = 0;
+  // ---- second sighting of this signature: capture the launches into a graph (first sighting runs eagerly: it also performs the
+  // one-time initialisations - function attributes, driver entry points - that must not happen inside a capture)
+  if (graphable && m->seen[key]++ >= 1) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      rc = fn(c);
+      const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+      cudaGraphExec_t exec = nullptr;
+      if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        if (m->graphs.size() >= kMaxGraphs) {   // evict the least recently used
+          size_t lru = 0;
+          for (size_t i = 1; i < m->graphs.size(); ++i) if (m->graphs[i].tick < m->graphs[lru].tick) lru = i;
+          cudaGraphExecDestroy(m->graphs[lru].exec);
+          m->graphs.erase(m->graphs.begin() + lru);
+        }
+        se_model::GraphEntry e;
+        e.key = key; e.exec = exec; e.arena = m->arena; e.launches = g_launches; e.tick = ++m->tick;
+        m->graphs.push_back(e);
+        SE_CUDA_OK(cudaGraphLaunch(exec, stream));
+        return 0;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      m->seen[key] = -1000000;   // not capturable: stay eager for this signature
+      if (rc) return rc;
+      c.arena.reset((char*)m->arena);
+      g_launches = 0;
+    }
+  }
   return fn(c);
 }
 
@@ -1085,6 +1141,7 @@ void se_model_destroy(se_model* m) {
   for (void* p : m->owned) cudaFree(p);
   if (m->arena) cudaFree(m->arena);
   if (m->order_ev) cudaEventDestroy(m->order_ev);
+  for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   delete m;
 }
 
@@ -1144,6 +1201,8 @@ static int forward_inference(se_model* m, const float* image, const float* sketc
   SE_REQUIRE(image && sketch && composed && mask, "null tensor");
   int rc = check_hw(H, W);
   if (rc) return rc;
+  std::vector<uintptr_t> key = {1, (uintptr_t)H, (uintptr_t)W, (uintptr_t)image, (uintptr_t)sketch, (uintptr_t)composed, (uintptr_t)mask, (uintptr_t)composed_bs,
+                                (uintptr_t)mask_bs, (uintptr_t)coarse, (uintptr_t)fine, (uintptr_t)mask_image, (uintptr_t)mask_bin_in, (uintptr_t)mask_bin_out};
   return with_arena(m, precision, B, st, [&](Ctx& c) -> int {
     Buf mb = c.get((size_t)B * H * W * 4);
     int r = run_netM(c, image, sketch, H, W, mask, mask_image, (float*)mb.p, mask_bs);
@@ -1158,7 +1217,7 @@ static int forward_inference(se_model* m, const float* image, const float* sketc
     if (r) return r;
     c.put(mb);
     return 0;
-  });
+  }, key);
 }
 
 int se_forward_inference(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision, float* composed,
@@ -1181,7 +1240,8 @@ int se_netM_forward(se_model* m, const float* x, const float* guide, int B, int 
   SE_REQUIRE(x && guide && mask1, "null tensor");
   int rc = check_hw(H, W);
   if (rc) return rc;
-  return with_arena(m, precision, B, (cudaStream_t)stream, [&](Ctx& c) -> int { return run_netM(c, x, guide, H, W, mask1, x_stage1, nullptr); });
+  return with_arena(m, precision, B, (cudaStream_t)stream, [&](Ctx& c) -> int { return run_netM(c, x, guide, H, W, mask1, x_stage1, nullptr); },
+                    {2, (uintptr_t)H, (uintptr_t)W, (uintptr_t)x, (uintptr_t)guide, (uintptr_t)mask1, (uintptr_t)x_stage1});
 }
 
 int se_netG_forward(se_model* m, const float* x, const float* x2, const float* mask, const float* mask2, const float* guide, int B, int H,
@@ -1190,7 +1250,8 @@ int se_netG_forward(se_model* m, const float* x, const float* x2, const float* m
   int rc = check_hw(H, W);
   if (rc) return rc;
   return with_arena(m, precision, B, (cudaStream_t)stream,
-                    [&](Ctx& c) -> int { return run_netG(c, x, x2, mask, mask2, guide, H, W, x_stage1, x_stage2, nullptr, nullptr, nullptr); });
+                    [&](Ctx& c) -> int { return run_netG(c, x, x2, mask, mask2, guide, H, W, x_stage1, x_stage2, nullptr, nullptr, nullptr); },
+                    {3, (uintptr_t)H, (uintptr_t)W, (uintptr_t)x, (uintptr_t)x2, (uintptr_t)mask, (uintptr_t)mask2, (uintptr_t)guide, (uintptr_t)x_stage1, (uintptr_t)x_stage2});
 }
 
 int se_gated_conv_forward(se_model* m, char net, const char* layer, const float* x, int B, int H, int W, int precision, float* y,

@@ -23,7 +23,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity, const char* what) {
+static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity, const char* what) {
   printf("sketchedit_b200: %s timeout tag=%d block=%d thread=%d parity=%u\n", what, tag, blockIdx.x, threadIdx.x, parity);
   __trap();
 }
