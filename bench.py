@@ -364,20 +364,30 @@ def run_b200(args):
         step_e2e()
     e2e_serial = world * B * args.steps / timed(lambda: [step_e2e() for _ in range(args.steps)])
 
-    # (b) the package's pipelined loop over the same batches (models.EditLine2Model.inference_stream): every step
-    # copies its own inputs host->device and its own outputs device->host on side streams; with N > 1 ranks every step's
-    # outputs also go through the all-gather (gather=...) before they are copied out
-    def run_stream(n):
-        with torch.no_grad():
-            for comp, msk in model.inference_stream(({"image": img_h, "mask": sk_h} for _ in range(n)), gather=gather):
-                pass
-        return comp, msk
+    # (b) the package's pipelined loop over the same batches (models.EditLine2Model.inference_stream): every step copies its
+    # own inputs host->device and its own outputs device->host on side streams. N = 1: the uint8 form (the codecs of the
+    # reference's dataset / test.py run on the device: uint8 pixels in, uint8 BGR + mask out - what test.py drives). N > 1:
+    # float tensors, and every step's outputs also go through the all-gather (gather=...) before they are copied out
+    img_u8 = ((img_h.permute(0, 2, 3, 1) + 1) / 2 * 255).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+    sk_u8 = (sk_h[:, 0] * 255).to(torch.uint8).contiguous().pin_memory()
 
-    run_stream(6)   # > depth + 2 batches: the pinned output ring is allocated (cudaHostAlloc is slow) before the timed loop
-    e2e_value = world * B * args.steps / timed(lambda: run_stream(args.steps))
+    def run_stream(n, u8):
+        batch = {"image_u8": img_u8, "mask_u8": sk_u8} if u8 else {"image": img_h, "mask": sk_h}
+        with torch.no_grad():
+            for a, b in model.inference_stream((batch for _ in range(n)), gather=None if u8 else gather, uint8=u8):
+                pass
+        return a, b
+
+    use_u8 = world == 1
+    run_stream(6, use_u8)   # > depth + 2 batches: the pinned output ring is allocated (cudaHostAlloc is slow) before the timed loop
+    e2e_value = world * B * args.steps / timed(lambda: run_stream(args.steps, use_u8))
+    e2e_float = None
+    if use_u8:
+        run_stream(6, False)
+        e2e_float = world * B * args.steps / timed(lambda: run_stream(args.steps, False))
     clocks = sampler.stop() if rank == 0 else None
-    h2d = B * 4 * H * W * 4
-    d2h = B * 4 * H * W * 4
+    h2d = B * H * W * (4 if use_u8 else 16)
+    d2h = B * H * W * (4 if use_u8 else 16)
 
     # ---------------- one instrumented pass for the roofline table (CUDA events around every launch)
     roof = rows = None
@@ -434,8 +444,13 @@ def run_b200(args):
                                      "%.2f GFLOP/img are not executed and not counted in roofline.achieved" % (dead_flops_per_image(H, W) / 1e9)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "models.create_model(opt).inference_stream(batches): pinned CPU tensors in -> pinned CPU outputs, "
-                           "per-step H2D/D2H on side streams overlapping compute" + ("; outputs all-gathered over NCCL every step" if world > 1 else ""),
+                    "api": ("models.create_model(opt).inference_stream(batches, uint8=True): pinned uint8 pixels in (dataset format before "
+                            "ToTensor/Normalize) -> pinned uint8 BGR + mask out (test.py's output format), codecs on the device, per-step H2D/D2H "
+                            "on side streams overlapping compute") if use_u8 else
+                           ("models.create_model(opt).inference_stream(batches, gather=...): pinned float CPU tensors in -> pinned CPU outputs, "
+                            "per-step H2D/D2H on side streams; outputs all-gathered over NCCL every step"),
+                    "float_value": e2e_float,
+                    "float_api": "same stream API with fp32 tensors (16 B per pixel each way)" if use_u8 else None,
                     "serial_value": e2e_serial,
                     "serial_api": "models.create_model(opt)(data, mode='inference') + .copy_ to pinned CPU, one blocking call per batch"},
             "gpu_launches": launches_per_step * args.steps,

@@ -68,6 +68,13 @@ int se_forward_inference(se_model* m, const float* image, const float* sketch, i
 int se_forward_inference_packed(se_model* m, const float* image, const float* sketch, int B, int H, int W, int precision,
                                 float* packed, void* stream);
 
+/* Same forward with the host-side codecs of the reference's test flow moved onto the device: inputs as the dataset reads them
+ * before ToTensor/Normalize (reference data/testimage_dataset.py:89-103: image_u8 [B,H,W,3] RGB, sketch_u8 [B,H,W] already resized
+ * to the image; on device: x/255 -> (x-0.5)/0.5, sketch > 0), outputs as test.py writes them (reference test.py:25-35:
+ * ((x+1)/2*255) and (mask*255) truncated to uint8, HWC, RGB->BGR): bgr_u8 [B,H,W,3], mask_u8 [B,H,W]. 4x fewer bytes each way. */
+int se_forward_inference_u8(se_model* m, const unsigned char* image_u8, const unsigned char* sketch_u8, int B, int H, int W,
+                            int precision, unsigned char* bgr_u8, unsigned char* mask_u8, void* stream);
+
 /* ---- netM: replaces MDGenerator.forward(x, guide) -> (mask1, x_stage1)  (editline2_g.py:59-94) */
 int se_netM_forward(se_model* m, const float* x, const float* guide, int B, int H, int W, int precision, float* mask1,
                     float* x_stage1 /* may be NULL */, void* stream);

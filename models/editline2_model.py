@@ -75,14 +75,20 @@ class EditLine2Model(torch.nn.Module):
                     "composed": composed}
         raise ValueError("|mode| is invalid or training-only: %r" % (mode,))
 
-    def inference_stream(self, loader, depth=2, pinned_ring=True, gather=None):
+    def inference_stream(self, loader, depth=2, pinned_ring=True, gather=None, uint8=False, with_data=False):
         """Pipelined form of ``for data in loader: model(data, mode='inference')`` for throughput serving.
 
         Yields ``(composed, mask)`` per batch, in order, as PINNED CPU tensors (views of one packed [B,4,H,W] host
         buffer). The host->device copy of batch i+1 and the device->host copy of batch i-1 run on their own CUDA
         streams while batch i computes (``depth`` device buffers per tensor), so a step costs max(copy, compute)
-        instead of their sum. Batches whose 'image'/'mask' tensors are in pinned memory (DataLoader(pin_memory=True))
-        overlap fully.
+        instead of their sum. Batches whose input tensors are in pinned memory (DataLoader(pin_memory=True)) overlap fully.
+
+        uint8=True: the reference's host-side codecs run on the device (``Engine.inference_u8``): a batch supplies
+        ``data['image_u8']`` [B,H,W,3] RGB uint8 and ``data['mask_u8']`` [B,H,W] uint8 (what the dataset holds before
+        ToTensor/Normalize, reference data/testimage_dataset.py:89-103) and the results are ``(bgr_u8 [B,H,W,3], mask_u8
+        [B,H,W])`` exactly as test.py:25-35 writes them: 4x fewer bytes over PCIe in each direction.
+
+        with_data=True: yield ``(out0, out1, data)`` (test.py needs the batch's output paths).
 
         pinned_ring=True (default): results are views of a ring of ``depth + 2`` pinned buffers handed out round robin. The
         copy of batch i + depth - 1 is already in flight when result i is drawn, so a result stays intact while at most
@@ -90,13 +96,13 @@ class EditLine2Model(torch.nn.Module):
         pinned_ring=False allocates fresh pinned tensors for every batch (a cudaHostAlloc per batch when the host
         allocator cannot recycle, which costs more than the copy itself).
 
-        gather: a ``sketchedit_b200.parallel.OutputGather`` (data-parallel serving, one process per GPU): every batch's
-        packed outputs are written into this rank's slice of the gather buffer and all-gathered over NCCL (async, in
+        gather: a ``sketchedit_b200.parallel.OutputGather`` (data-parallel serving, one process per GPU; float mode): every
+        batch's packed outputs are written into this rank's slice of the gather buffer and all-gathered over NCCL (async, in
         place) before this rank's shard is copied to the host; all ranks must feed equal batch sizes."""
         import collections
         eng = self.engine()
-        if gather is not None and gather.depth != depth:
-            raise ValueError("gather ring depth must equal the stream depth (%d)" % depth)
+        if gather is not None and (gather.depth != depth or uint8):
+            raise ValueError("gather= needs float mode and a ring depth equal to the stream depth (%d)" % depth)
         dev = torch.device("cuda")
         cur = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -104,32 +110,44 @@ class EditLine2Model(torch.nn.Module):
         pending = collections.deque()
         ring = {}        # (B, H, W) -> [buffers, results handed out so far]
 
+        def new_host(B, H, W):
+            if uint8:
+                return (torch.empty(B, H, W, 3, dtype=torch.uint8, pin_memory=True), torch.empty(B, H, W, dtype=torch.uint8, pin_memory=True))
+            packed = torch.empty(B, 4, H, W, pin_memory=True)
+            return (packed,)
+
         def host_out(B, H, W):
             if not pinned_ring:
-                return torch.empty(B, 4, H, W, pin_memory=True)
+                return new_host(B, H, W)
             entry = ring.setdefault((B, H, W), [[], 0])
             bufs, count = entry
             if len(bufs) < depth + 2:
-                bufs.append(torch.empty(B, 4, H, W, pin_memory=True))
+                bufs.append(new_host(B, H, W))
             entry[1] = count + 1
             return bufs[count % (depth + 2)]       # strict round robin per shape: 0, 1, .., depth+1, 0, 1, ..
 
         def drain_one():
-            packed_h, ev = pending.popleft()
+            host, ev, data = pending.popleft()
             ev.synchronize()
-            return packed_h[:, :3], packed_h[:, 3:4]
+            res = (host[0], host[1]) if uint8 else (host[0][:, :3], host[0][:, 3:4])
+            return res + (data,) if with_data else res
 
+        in_keys = ("image_u8", "mask_u8") if uint8 else ("image", "mask")
         for i, data in enumerate(loader):
-            img_h, line_h = data["image"], data["mask"]
-            B, _, H, W = img_h.shape
+            img_h, line_h = data[in_keys[0]], data[in_keys[1]]
+            B, H, W = (img_h.shape[0], img_h.shape[1], img_h.shape[2]) if uint8 else (img_h.shape[0], img_h.shape[2], img_h.shape[3])
             slot = slots[i % depth]
             if slot is None or slot["shape"] != (B, H, W):
                 if slot is not None:   # shape change (ragged last batch): let the old buffers' users finish first
                     slot["ev_comp"].synchronize()
                     slot["ev_out"].synchronize()
-                new = lambda c: torch.empty(B, c, H, W, device=dev, dtype=torch.float32)
-                slot = {"shape": (B, H, W), "img": new(3), "line": new(1), "packed": None if gather is not None else new(4),
-                        "ev_in": torch.cuda.Event(), "ev_comp": torch.cuda.Event(), "ev_out": torch.cuda.Event()}
+                if uint8:
+                    u8 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.uint8)
+                    bufs = {"img": u8(B, H, W, 3), "line": u8(B, H, W), "out": (u8(B, H, W, 3), u8(B, H, W))}
+                else:
+                    f32 = lambda c: torch.empty(B, c, H, W, device=dev, dtype=torch.float32)
+                    bufs = {"img": f32(3), "line": f32(1), "out": None if gather is not None else (f32(4),)}
+                slot = dict(bufs, shape=(B, H, W), ev_in=torch.cuda.Event(), ev_comp=torch.cuda.Event(), ev_out=torch.cuda.Event())
                 slots[i % depth] = slot
             s_in.wait_event(slot["ev_comp"])           # the previous user of these input buffers has been computed
             with torch.cuda.stream(s_in):
@@ -147,19 +165,23 @@ class EditLine2Model(torch.nn.Module):
                 slot["ev_comp"].record(cur)            # inputs are free again; the outputs follow the collective:
                 with torch.cuda.stream(s_out):
                     gather.wait(k)                     # s_out waits for the all-gather of this batch
-                    src = gather.bufs[k][gather.rank * B:(gather.rank + 1) * B]
+                    src = (gather.bufs[k][gather.rank * B:(gather.rank + 1) * B],)
             else:
-                eng.inference_packed(slot["img"], slot["line"], precision=self.precision, out=slot["packed"])
+                if uint8:
+                    eng.inference_u8(slot["img"], slot["line"], precision=self.precision, out=slot["out"])
+                else:
+                    eng.inference_packed(slot["img"], slot["line"], precision=self.precision, out=slot["out"][0])
                 slot["ev_comp"].record(cur)
                 s_out.wait_event(slot["ev_comp"])
-                src = slot["packed"]
+                src = slot["out"]
             with torch.cuda.stream(s_out):
-                packed_h = host_out(B, H, W)
-                packed_h.copy_(src, non_blocking=True)
+                host = host_out(B, H, W)
+                for h_t, d_t in zip(host, src):
+                    h_t.copy_(d_t, non_blocking=True)
                 slot["ev_out"].record(s_out)
                 done = torch.cuda.Event()
                 done.record(s_out)
-            pending.append((packed_h, done))
+            pending.append((host, done, data))
             if len(pending) >= depth:
                 yield drain_one()
         while pending:

@@ -721,7 +721,8 @@ static std::vector<std::string> with_prefix(const std::string& pfx, std::initial
 // out_bs / msoft_bs: elements between images of out_nchw / mask_soft (0 = dense); non-zero when they are views into a packed
 // [B,4,H,W] output (se_forward_inference_packed)
 static int run_head(Ctx& c, char net, const std::string& name, const View& in, int mode, const float* img, const float* mask_bin,
-                    const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, long long out_bs = 0, long long msoft_bs = 0) {
+                    const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, long long out_bs = 0, long long msoft_bs = 0,
+                    unsigned char* out_u8 = nullptr) {
   Layer* L = find_ready(c.m, net, name);
   SE_REQUIRE(L != nullptr && L->is_head, "head layer " + name + ": " + last_error());
   {
@@ -736,11 +737,11 @@ static int run_head(Ctx& c, char net, const std::string& name, const View& in, i
   }
   if (in.c8 == 1 && c.act_dt() == DT_BF16) {
     CK(head_c8(in.p, L->w_head_host.data(), L->b_host.data(), L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
-               out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, out_bs, msoft_bs, c.stream));
+               out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, out_bs, msoft_bs, out_u8, c.stream));
     return 0;
   }
   CK(head(in.p, c.act_dt(), in.c8, L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
-          out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, out_bs, msoft_bs, c.stream));
+          out_pack8, c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, out_bs, msoft_bs, out_u8, c.stream));
   return 0;
 }
 
@@ -879,7 +880,8 @@ static const std::initializer_list<const char*> kTrunk9 = {"conv1", "conv2_downs
 
 // MDGenerator.forward: x [B,3,H,W], guide [B,1,H,W] -> mask1 (soft, NCHW), optional x_stage1; also the
 // binarised mask plane (mask1 > 0.5) when mask_bin != nullptr.
-static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, float* mask1, float* x_stage1, float* mask_bin, long long mask1_bs = 0) {
+static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, float* mask1, float* x_stage1, float* mask_bin, long long mask1_bs = 0,
+                    unsigned char* mask_u8 = nullptr) {
   const int dt = c.act_dt();
   Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * c.esz());
   c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
@@ -907,7 +909,7 @@ static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, fl
   Buf scratch;
   float* mb = mask_bin;
   if (!mb) { scratch = c.get((size_t)c.B * H * W * 4); mb = (float*)scratch.p; }
-  rc = run_head(c, 'M', "conv_mask_17", v, HEAD_MASK, nullptr, nullptr, nullptr, mask1, mb, nullptr, mask1_bs);
+  rc = run_head(c, 'M', "conv_mask_17", v, HEAD_MASK, nullptr, nullptr, nullptr, mask1, mb, nullptr, mask1_bs, 0, mask_u8);
   if (rc) return rc;
   c.put(scratch);
   c.put(b);
@@ -918,7 +920,7 @@ static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, fl
 // Outputs: x_stage1 (optional), x_stage2 (optional NCHW), composed (optional: fine*soft + img*(1-soft)).
 static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, const float* mask2, const float* guide, int H, int W,
                     float* x_stage1, float* x_stage2, float* composed, const float* mask_soft, const float* blend_img,
-                    long long composed_bs = 0, long long msoft_bs = 0) {
+                    long long composed_bs = 0, long long msoft_bs = 0, unsigned char* composed_u8 = nullptr) {
   // guide == nullptr: the reference's guide=None -> an all-ones sketch channel (editline_g.py:127-130), built by pack8
   const int dt = c.act_dt();
   const int* opt = c.m->opt;
@@ -1006,8 +1008,8 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     int rc = run_chain(c, 'G', with_prefix("allconv", {"11", "12", "13_upsample_conv", "14", "15_upsample_conv", "16"}),
                        cat_view(cat2.p), true, cat2, &v16, &b16);
     if (rc) return rc;
-    if (composed) {
-      rc = run_head(c, 'G', "allconv17", v16, HEAD_FINE, blend_img, nullptr, mask_soft, composed, x_stage2, nullptr, composed_bs, msoft_bs);
+    if (composed || composed_u8) {
+      rc = run_head(c, 'G', "allconv17", v16, HEAD_FINE, blend_img, nullptr, mask_soft, composed, x_stage2, nullptr, composed_bs, msoft_bs, composed_u8);
     } else {
       rc = run_head(c, 'G', "allconv17", v16, HEAD_TANH, nullptr, nullptr, nullptr, x_stage2, nullptr, nullptr);
     }
@@ -1233,6 +1235,29 @@ int se_forward_inference_packed(se_model* m, const float* image, const float* sk
   const long long bs = 4LL * H * W;   // [B,4,H,W]: composed in channels 0-2, the soft mask in channel 3
   return forward_inference(m, image, sketch, B, H, W, precision, packed, packed + 3LL * H * W, bs, bs, nullptr, nullptr, nullptr, nullptr, nullptr,
                            (cudaStream_t)stream);
+}
+
+int se_forward_inference_u8(se_model* m, const unsigned char* image_u8, const unsigned char* sketch_u8, int B, int H, int W, int precision,
+                            unsigned char* bgr_u8, unsigned char* mask_u8, void* stream) {
+  SE_REQUIRE(image_u8 && sketch_u8 && bgr_u8 && mask_u8, "null tensor");
+  int rc = check_hw(H, W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<uintptr_t> key = {4, (uintptr_t)H, (uintptr_t)W, (uintptr_t)image_u8, (uintptr_t)sketch_u8, (uintptr_t)bgr_u8, (uintptr_t)mask_u8};
+  return with_arena(m, precision, B, st, [&](Ctx& c) -> int {
+    // input codec (reference data/testimage_dataset.py:89-103) -> the usual forward -> output codec fused into the two heads
+    // (test.py:25-35): the float image / masks live only in the workspace
+    Buf img = c.get((size_t)B * 3 * H * W * 4), sk = c.get((size_t)B * H * W * 4), soft = c.get((size_t)B * H * W * 4), mb = c.get((size_t)B * H * W * 4);
+    c.tag("u8_to_inputs_kernel|input codec", 0, 0, 0, (double)B * H * W * (4 + 16));
+    CK(u8_to_inputs(image_u8, sketch_u8, (float*)img.p, (float*)sk.p, B, H, W, st));
+    int r = run_netM(c, (const float*)img.p, (const float*)sk.p, H, W, (float*)soft.p, nullptr, (float*)mb.p, 0, mask_u8);
+    if (r) return r;
+    r = run_netG(c, (const float*)img.p, (const float*)img.p, (const float*)mb.p, (const float*)mb.p, (const float*)sk.p, H, W, nullptr, nullptr, nullptr,
+                 (const float*)soft.p, (const float*)img.p, 0, 0, bgr_u8);
+    if (r) return r;
+    c.put(mb); c.put(soft); c.put(sk); c.put(img);
+    return 0;
+  }, key);
 }
 
 int se_netM_forward(se_model* m, const float* x, const float* guide, int B, int H, int W, int precision, float* mask1, float* x_stage1,

@@ -79,7 +79,8 @@ template <typename T, int COUT>
 __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w /*[9][12][COUT]*/, const float* __restrict__ bias,
                             int B, int H, int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
                             const float* __restrict__ mask_soft, float* __restrict__ out_nchw, float* __restrict__ out2,
-                            T* __restrict__ out_pack8, int no_mask_coarse, int Wp, int padl, int in_c8, long long obs, long long msbs) {
+                            T* __restrict__ out_pack8, int no_mask_coarse, int Wp, int padl, int in_c8, long long obs, long long msbs,
+                            unsigned char* __restrict__ out_u8) {
   // obs: elements between images of out_nchw (COUT*HW when dense; 4*HW when it is a view into a packed [B,4,H,W] output);
   // msbs: likewise for mask_soft
   __shared__ float ws[9 * 12 * COUT + COUT];
@@ -120,6 +121,7 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
     const float s = 1.0f / (1.0f + expf(-acc[0]));
     out_nchw[b * obs + pix] = s;
     out2[i] = s > 0.5f ? 1.0f : 0.0f;
+    if (out_u8) out_u8[i] = (unsigned char)(int)(s * 255.0f);   // test.py:25: (mask * 255).astype(uint8)
     return;
   }
   float t3[COUT];
@@ -144,7 +146,9 @@ __global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
       if (out2) out2[(b * COUT + o) * HW + pix] = t3[o];
-      out_nchw[b * obs + o * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      const float cv = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      if (out_nchw) out_nchw[b * obs + o * HW + pix] = cv;
+      if (out_u8) out_u8[i * 3 + (2 - o)] = (unsigned char)(int)((cv + 1.0f) / 2.0f * 255.0f);   // test.py:26-35: truncate, HWC, RGB -> BGR
     }
   }
 }
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
                                                       int W, int mode, const float* __restrict__ img, const float* __restrict__ mask_bin,
                                                       const float* __restrict__ mask_soft, float* __restrict__ out_nchw,
                                                       float* __restrict__ out2, __nv_bfloat16* __restrict__ out_pack8, int no_mask_coarse,
-                                                      int Wp, int padl, long long obs, long long msbs) {
+                                                      int Wp, int padl, long long obs, long long msbs, unsigned char* __restrict__ out_u8) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long HW = (long long)H * W;
   if (i >= B * HW) return;
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
     const float sg = 1.0f / (1.0f + expf(-r[0]));
     out_nchw[b * obs + pix] = sg;
     out2[i] = sg > 0.5f ? 1.0f : 0.0f;
+    if (out_u8) out_u8[i] = (unsigned char)(int)(sg * 255.0f);   // test.py:25: (mask * 255).astype(uint8)
     return;
   }
   float t3[COUT];
@@ -231,7 +236,9 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
 #pragma unroll
     for (int o = 0; o < COUT; ++o) {
       if (out2) out2[(b * COUT + o) * HW + pix] = t3[o];
-      out_nchw[b * obs + o * HW + pix] = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      const float cv = t3[o] * m + img[(b * 3 + o) * HW + pix] * (1.0f - m);
+      if (out_nchw) out_nchw[b * obs + o * HW + pix] = cv;
+      if (out_u8) out_u8[i * 3 + (2 - o)] = (unsigned char)(int)((cv + 1.0f) / 2.0f * 255.0f);   // test.py:26-35: truncate, HWC, RGB -> BGR
     }
   }
 }
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(128) head_c8_kernel(const __nv_bfloat16* __res
 template <int COUT>
 static int head_c8_launch(const void* x, const float* w_host, const float* b_host, int B, int H, int W, int mode, const float* img,
                           const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
-                          int Wp, int padl, long long obs, long long msbs, cudaStream_t s) {
+                          int Wp, int padl, long long obs, long long msbs, unsigned char* out_u8, cudaStream_t s) {
   HeadWeights<COUT> hw;
   for (int t = 0; t < 9; ++t)
     for (int p = 0; p < 6; ++p)
@@ -248,31 +255,31 @@ static int head_c8_launch(const void* x, const float* w_host, const float* b_hos
   const long long n = (long long)B * H * W;
   head_c8_kernel<COUT><<<cdiv(n, 128), 128, 0, s>>>((const __nv_bfloat16*)x, hw, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2,
                                                     (__nv_bfloat16*)out_pack8, no_mask_coarse, Wp, padl, obs ? obs : (long long)COUT * H * W,
-                                                    msbs ? msbs : (long long)H * W);
+                                                    msbs ? msbs : (long long)H * W, out_u8);
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }
 // w_host / b_host: host copies of the [9][12][cout] weights and the bias (kernel parameters are built from them)
 int head_c8(const void* x, const float* w_host, const float* b_host, int cout, int B, int H, int W, int mode, const float* img,
             const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse, int Wp, int padl,
-            long long obs, long long msbs, cudaStream_t s) {
+            long long obs, long long msbs, unsigned char* out_u8, cudaStream_t s) {
   SE_REQUIRE(cout == 1 || cout == 3, "head cout");
-  if (cout == 1) return head_c8_launch<1>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, obs, msbs, s);
-  return head_c8_launch<3>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, obs, msbs, s);
+  if (cout == 1) return head_c8_launch<1>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, obs, msbs, out_u8, s);
+  return head_c8_launch<3>(x, w_host, b_host, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8, no_mask_coarse, Wp, padl, obs, msbs, out_u8, s);
 }
 
 int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
-         int Wp, int padl, long long obs, long long msbs, cudaStream_t s) {
+         int Wp, int padl, long long obs, long long msbs, unsigned char* out_u8, cudaStream_t s) {
   const long long n = (long long)B * H * W;
   SE_REQUIRE(cout == 1 || cout == 3, "head cout");
   if (!obs) obs = (long long)cout * H * W;
   if (!msbs) msbs = (long long)H * W;
   SE_DISPATCH_T(dt, {
     if (cout == 1)
-      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8, obs, msbs);
+      head_kernel<T, 1><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8, obs, msbs, out_u8);
     else
-      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8, obs, msbs);
+      head_kernel<T, 3><<<cdiv(n, 128), 128, 0, s>>>((const T*)x, w, bias, B, H, W, mode, img, mask_bin, mask_soft, out_nchw, out2, (T*)out_pack8, no_mask_coarse, Wp, padl, in_c8, obs, msbs, out_u8);
   });
   SE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -891,6 +898,24 @@ int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo,
 int nhwc_to_nchw(const void* x, int dt, float* y, int B, int C, int HW, int ldx, int choff, cudaStream_t s) {
   const long long total = (long long)B * C * HW;
   SE_DISPATCH_T(dt, (nhwc_to_nchw_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)x, y, C, HW, ldx, choff, total)));
+  SE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// reference data/testimage_dataset.py:89-103 on device: image uint8 HWC RGB -> fp32 NCHW (ToTensor: /255; Normalize(0.5, 0.5)),
+// sketch uint8 (already resized to the image) -> {0, 1} fp32 (ToTensor then > 0)
+__global__ void u8_to_inputs_kernel(const unsigned char* __restrict__ img_u8, const unsigned char* __restrict__ sk_u8, float* __restrict__ img,
+                                    float* __restrict__ sk, int B, long long HW) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const long long b = i / HW, pix = i % HW;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) img[(b * 3 + c) * HW + pix] = (__fdiv_rn((float)img_u8[i * 3 + c], 255.0f) - 0.5f) / 0.5f;
+  sk[i] = sk_u8[i] > 0 ? 1.0f : 0.0f;
+}
+int u8_to_inputs(const unsigned char* img_u8, const unsigned char* sk_u8, float* img, float* sk, int B, int H, int W, cudaStream_t s) {
+  const long long HW = (long long)H * W;
+  u8_to_inputs_kernel<<<cdiv(B * HW, 256), 256, 0, s>>>(img_u8, sk_u8, img, sk, B, HW);
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -12,10 +12,11 @@ int pack8(const float* img, const float* sketch, const float* mask, void* out, i
           int img_mode, float sketch_scale, int write_mask, cudaStream_t s);
 int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
-         int Wp, int padl, long long out_bstride, long long msoft_bstride, cudaStream_t s);   // strides: elements between images, 0 = dense
+         int Wp, int padl, long long out_bstride, long long msoft_bstride, unsigned char* out_u8,
+         cudaStream_t s);   // strides: elements between images, 0 = dense; out_u8: HEAD_MASK -> mask bytes [B,H,W], HEAD_FINE -> BGR HWC bytes
 int head_c8(const void* x, const float* w_host, const float* b_host, int cout, int B, int H, int W, int mode, const float* img,
             const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse, int Wp, int padl,
-            long long out_bstride, long long msoft_bstride, cudaStream_t s);
+            long long out_bstride, long long msoft_bstride, unsigned char* out_u8, cudaStream_t s);
 int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int c8, int mode, float* out, cudaStream_t s);
 int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, int c8, cudaStream_t s);
 int avgpool4(const float* m, float* out, int B, int H, int W, cudaStream_t s);
@@ -31,6 +32,7 @@ int nchw_to_c8(const float* x, void* y, int B, int C, int HW, cudaStream_t s);
 int c8_to_nchw(const void* x, float* y, int B, int C, int HW, cudaStream_t s);
 int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo, int choff, cudaStream_t s);
 int nhwc_to_nchw(const void* x, int dt, float* y, int B, int C, int HW, int ldx, int choff, cudaStream_t s);
+int u8_to_inputs(const unsigned char* img_u8, const unsigned char* sk_u8, float* img, float* sk, int B, int H, int W, cudaStream_t s);
 int to_uint8(const float* comp, const float* mask, unsigned char* bgr, unsigned char* mk, int B, int H, int W, cudaStream_t s);
 long long count_nonfinite_bf16(const void* x, long long n, cudaStream_t s);
 int fill_zero(void* p, size_t bytes, cudaStream_t s);

@@ -144,6 +144,29 @@ class Engine:
                                                         _stream()))
         return packed
 
+    def inference_u8(self, image_u8, sketch_u8, precision="bf16", out=None):
+        """Forward with the reference's host-side codecs on the device: image_u8 [B,H,W,3] RGB uint8 and sketch_u8 [B,H,W]
+        uint8 (reference data/testimage_dataset.py:89-103 up to ToTensor) -> (bgr_u8 [B,H,W,3], mask_u8 [B,H,W]) exactly as
+        test.py:25-35 writes them. ``out=(bgr, mask)`` writes into caller-owned uint8 CUDA tensors."""
+        for t, nm in ((image_u8, "image_u8"), (sketch_u8, "sketch_u8")):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()):
+                raise _lib.SketchEditB200Error("%s must be a contiguous CUDA uint8 tensor" % nm)
+        B, H, W, C = image_u8.shape
+        if C != 3 or tuple(sketch_u8.shape) != (B, H, W):
+            raise _lib.SketchEditB200Error("image_u8 must be [B,H,W,3] and sketch_u8 [B,H,W]")
+        if out is None:
+            bgr = torch.empty(B, H, W, 3, device=image_u8.device, dtype=torch.uint8)
+            mk = torch.empty(B, H, W, device=image_u8.device, dtype=torch.uint8)
+        else:
+            bgr, mk = out
+            for t, shp in ((bgr, (B, H, W, 3)), (mk, (B, H, W))):
+                if not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and tuple(t.shape) == shp):
+                    raise _lib.SketchEditB200Error("out tensors must be contiguous CUDA uint8 [B,H,W,3] and [B,H,W]")
+        self._on_device(image_u8, sketch_u8, bgr, mk)
+        _lib.check(self.lib.se_forward_inference_u8(self.h, _ptr(image_u8), _ptr(sketch_u8), B, H, W, _lib.PREC[precision], _ptr(bgr), _ptr(mk),
+                                                    _stream()))
+        return bgr, mk
+
     def netM(self, x, guide, precision="bf16", want_image=True):
         x, guide = _chk_in(x), _chk_in(guide)
         B, _, H, W = x.shape

@@ -10,7 +10,6 @@ import torch
 import data
 import models
 from options.test_options import TestOptions
-from sketchedit_b200.engine import outputs_to_uint8
 
 
 def main(argv=None):
@@ -18,18 +17,24 @@ def main(argv=None):
     dataloader = data.create_dataloader(opt)
     model = models.create_model(opt)
     model.eval()
-    for i, batch in enumerate(dataloader):
-        if i * opt.batchSize >= opt.how_many:
-            break
-        with torch.no_grad():
-            generated, mask = model(batch, mode="inference")
-        bgr, mk = outputs_to_uint8(generated, mask)       # device-side (x+1)/2*255 -> uint8 HWC BGR
-        bgr, mk = bgr.cpu().numpy(), mk.cpu().numpy()
-        for b, path in enumerate(batch["path"]):
-            print("process image... %s" % path)
-            assert cv2.imwrite(os.path.join(opt.output_dir, path), bgr[b])
-            if getattr(opt, "output_mask_dir", None) is not None:
-                assert cv2.imwrite(os.path.join(opt.output_mask_dir, path), mk[b])
+
+    def batches():
+        for i, batch in enumerate(dataloader):
+            if i * opt.batchSize >= opt.how_many:
+                break
+            yield batch
+
+    # the reference loop (test.py:20-37: model(data_i, mode='inference') -> uint8 -> BGR -> imwrite), pipelined: copies of the
+    # neighbouring batches overlap the forward, and both codecs (normalise / binarise in, (x+1)/2*255 -> uint8 HWC BGR out) run
+    # on the device, so 4 bytes per pixel cross PCIe in each direction instead of 16
+    with torch.no_grad():
+        for bgr, mk, batch in model.inference_stream(batches(), uint8=True, with_data=True):
+            bgr, mk = bgr.numpy(), mk.numpy()
+            for b, path in enumerate(batch["path"]):
+                print("process image... %s" % path)
+                assert cv2.imwrite(os.path.join(opt.output_dir, path), bgr[b])
+                if getattr(opt, "output_mask_dir", None) is not None:
+                    assert cv2.imwrite(os.path.join(opt.output_mask_dir, path), mk[b])
 
 
 if __name__ == "__main__":

@@ -193,6 +193,42 @@ def test_test_py_end_to_end(prec, tmp_path):
             assert np.abs(got_m.astype(int) - rm[0].astype(int)).max() <= 1
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_uint8_codecs_on_device(prec):
+    """Engine.inference_u8 (input codec: x/255 -> (x-0.5)/0.5, sketch > 0; output codec fused into the heads) is byte for byte
+    the float forward on host-decoded inputs followed by the oracle's test.py conversion."""
+    rs = np.random.RandomState(5)
+    img_u8 = torch.from_numpy(rs.randint(0, 256, (2, 64, 96, 3), dtype=np.uint8))
+    _, sk = synth.synth_inputs(2, 64, 96, seed=44)
+    sk_u8 = (sk[:, 0] * 255).to(torch.uint8)
+    sk_u8[0, 10:14, 5:40] = 7          # any non-zero value is sketch (reference: ToTensor then > 0)
+    image = img_u8.permute(0, 3, 1, 2).float().div(255).sub(0.5).div(0.5)        # reference data/testimage_dataset.py:89-103
+    sketch = (sk_u8.float().div(255)[:, None] > 0).float()
+    eng = engine()
+    bgr, mk = eng.inference_u8(img_u8.cuda(), sk_u8.cuda(), precision=prec)
+    comp, mask, _ = eng.inference(image.cuda(), sketch.cuda(), precision=prec)
+    g, m = O.to_uint8_outputs(comp.cpu(), mask.cpu())
+    assert np.array_equal(bgr.cpu().numpy(), g.transpose(0, 2, 3, 1)[..., ::-1])
+    assert np.array_equal(mk.cpu().numpy(), m)
+
+
+def test_uint8_stream_matches_blocking_calls():
+    model = _model("bf16")
+    rs = np.random.RandomState(6)
+    batches = []
+    for i, b in enumerate((2, 2, 2, 1)):
+        _, sk = synth.synth_inputs(b, 64, 64, seed=70 + i)
+        batches.append({"image_u8": torch.from_numpy(rs.randint(0, 256, (b, 64, 64, 3), dtype=np.uint8)).pin_memory(),
+                        "mask_u8": (sk[:, 0] * 255).to(torch.uint8).pin_memory(), "tag": i})
+    eng = model.engine()
+    with torch.no_grad():
+        want = [tuple(t.cpu() for t in eng.inference_u8(d["image_u8"].cuda(), d["mask_u8"].cuda(), precision="bf16")) for d in batches]
+        got = [(a.clone(), b.clone(), d["tag"]) for a, b, d in model.inference_stream(iter(batches), uint8=True, with_data=True)]
+    assert [t for _, _, t in got] == [0, 1, 2, 3]
+    for (ga, gb, _), (wa, wb) in zip(got, want):
+        assert torch.equal(ga, wa) and torch.equal(gb, wb)
+
+
 def test_stream_ring_keeps_depth_plus_one_results():
     """inference_stream's pinned ring (depth + 2 buffers, strict round robin): the newest `depth + 1` results stay intact
     -- held WITHOUT cloning (the copy of batch i + depth - 1 is in flight when result i is drawn)."""
