@@ -80,6 +80,7 @@ struct ConvParams {
   int out_c8;           // 0: NHWC (pitch ldo, channel offset choff); 1: C8 = [N][ldo blocks][H][W][8], choff % 8 == 0 (bf16 only)
   int Hout, Wout, ldo, choff;
   int osy, ooy, osx, oox;
+  int out_blk_split, out_blk_jump, out_par_stride;   // fused layer pairs (EpiParams::blk_split ..); 0 = plain layer
   // epilogue
   int epi;
   float scale;                  // EPI_LINEAR
@@ -97,6 +98,10 @@ struct EpiParams {
   float scale;
   const float* colscale;
   int Cout, NT;
+  // two gated layers fused along N (stem pairs that read the same packed input): output blocks >= blk_split belong to the second
+  // layer's tensor, blk_jump (16 B units) further on; par_stride = channel blocks between the parity groups of a
+  // space-to-depth output (ldo / 4 unless two such tensors share the buffer). blk_split = 1 << 20: off.
+  int blk_split, blk_jump, par_stride;
   int has_bias;   // 0: the launch has no bias vector (attention GEMMs): no per-column constants are staged in shared memory
   int goff;   // gated epilogues: accumulator column of gate channel 0 (= Cout/2 rounded up to 8; the weight image
               // places feature c at column c and its gate at goff + c, columns in between are zero weights)

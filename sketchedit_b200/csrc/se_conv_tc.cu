@@ -291,6 +291,9 @@ void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
   e->epi = c.epi; e->scale = c.scale; e->colscale = c.colscale;
   e->Cout = c.Cout; e->NT = NT;
   e->has_bias = c.bias != nullptr ? 1 : 0;
+  e->blk_split = c.out_blk_split > 0 ? c.out_blk_split : (1 << 20);
+  e->blk_jump = c.out_blk_split > 0 ? c.out_blk_jump : 0;
+  e->par_stride = c.out_par_stride > 0 ? c.out_par_stride : (c.ldo >> 2);
   e->goff = (c.epi == EPI_LINEAR) ? 0 : gated_goff(c.Cout);
 }
 // the fast epilogue addresses the output in 32-bit units of 16 B

@@ -188,6 +188,8 @@ struct Layer {
   std::vector<float> w_host, b_host;
   std::vector<ClassW> cls;
   std::vector<C8Group> groups; // deconv layers on the tensor-core path: sub-pixel classes fused per launch (se_conv_c8.h)
+  int pair_cin_sum = 0;        // fused_pair: real input channels of the two source layers together (algorithmic FLOPs)
+  bool fused_pair = false;     // two 5x5 stems over the same packed input fused along N (tensor-core path; see make_stem_pair)
   float* bias = nullptr;       // device [cout]
   float* w_head = nullptr;     // device [9][12][cout] (heads)
   std::vector<float> w_head_host;   // same, host copy (kernel-parameter weights of the channel-blocked head kernel)
@@ -632,19 +634,26 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     cp.osy = cw.osy; cp.ooy = cw.ooy; cp.osx = cw.osx; cp.oox = cw.oox;
     cp.epi = s.act == 1 ? EPI_GATE_RELU : EPI_GATE_ELU;
     cp.scale = 1.0f; cp.colscale = nullptr;
+    if (L.fused_pair) {
+      // two space-to-depth tensors of 4 x 3 blocks each, back to back per image (ldo = 24 blocks): blocks 3..5 of the fused
+      // output are blocks 0..2 of the second one, 12 - 3 = 9 block planes further on
+      SE_REQUIRE(out_c8 == 2 && ldo == 24, "a fused stem pair writes two space-to-depth tensors");
+      cp.out_blk_split = 3; cp.out_par_stride = 3; cp.out_blk_jump = 9 * (cp.Hout / 2) * (cp.Wout / 2);
+    }
     if (g_timing && !c.dry) {
       // algorithmic work of this launch. A deconv layer is 4 sub-pixel class launches: each gets a quarter of the
       // reference op's 2*MAC (nearest x2 + 3x3 over the (2Ho x 2Wo) output) and issues 4 taps instead of 9.
       // (a fused launch carries `gc` classes)
       const double gc = grp ? grp->ncls : 1.0;
       const double pos = (double)c.B * Ho * Wo * gc, ncls = (double)L.cls.size() / gc;
-      const double f_alg = 2.0 * pos * s.cout * s.cin * (s.deconv ? 9.0 : (double)s.k * s.k);
-      const double f_exec = 2.0 * pos * s.cout * s.cin * (s.deconv ? 4.0 : (double)s.k * s.k);
-      const double bytes = ((double)c.B * in.H * in.W * s.cin / ncls + pos * (s.cout / 2) + (double)s.cout * s.cin * s.k * s.k / ncls) * c.esz();
+      const double cin_alg = L.fused_pair ? L.pair_cin_sum / 2.0 : (double)s.cin;   // a stem pair: two 48-output layers over their own channels
+      const double f_alg = 2.0 * pos * s.cout * cin_alg * (s.deconv ? 9.0 : (double)s.k * s.k);
+      const double f_exec = 2.0 * pos * s.cout * cin_alg * (s.deconv ? 4.0 : (double)s.k * s.k);
+      const double bytes = ((double)c.B * in.H * in.W * (L.fused_pair ? 8.0 : (double)s.cin) / ncls + pos * (s.cout / 2) + (double)s.cout * s.cin * s.k * s.k / ncls) * c.esz();
       const bool tcp = c.prec == SE_PREC_BF16_TC && cw.has_tc;
       char buf[160];
       snprintf(buf, sizeof(buf), "%s|%s %d->%d k%d s%d d%d @%dx%d", tcp ? (cw.use_c8 ? "conv_c8_kernel" : "conv_tc_kernel") : "conv_direct_kernel",
-               s.deconv ? (grp ? (grp->ncls == 4 ? "deconv (4 classes fused)" : "deconv (2 classes fused)") : "deconv-class") : "conv", s.cin, s.cout, s.k, s.stride, s.rate, Ho * cw.osy, Wo * cw.osx);
+               s.deconv ? (grp ? (grp->ncls == 4 ? "deconv (4 classes fused)" : "deconv (2 classes fused)") : "deconv-class") : (L.fused_pair ? "stem pair" : "conv"), s.cin, s.cout, s.k, s.stride, s.rate, Ho * cw.osy, Wo * cw.osx);
       c.tag(buf, tcp ? 1 : 0, f_alg, f_exec, bytes);
     }
     if (grp) CK(c8_launch(cp, cw.c8, c.stream, grp));
@@ -932,26 +941,32 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   const int cat_ld = tc ? 24 : 192;                    // 192-channel concat buffers: 24 channel blocks or pixel pitch 192
   auto cat_view = [&](void* p) { return tc ? c8view(p, h, w, 192, 24, 0) : nhwc(p, h, w, 192, 192); };
   Buf cat1 = c.get((size_t)c.B * h * w * 192 * e);
-  {
+  // stem pairs (tensor-core path, make_stem_pair): conv1 + wconv1 share one packed input when both encoders see the same image
+  // and mask (always true on the inference path: netG(inputs, inputs, mask_bin, mask_bin, line))
+  Layer* pair1 = (tc && x == x2 && mask == mask2) ? find_layer(c.m, 'G', "conv1+wconv1") : nullptr;
+  Layer* pair2 = tc ? find_layer(c.m, 'G', "xconv1+pmconv1") : nullptr;
+  const size_t pair_bytes = (size_t)c.B * 24 * (H / 2) * (W / 2) * 16;   // two space-to-depth tensors of 24 channels
+  auto pair_view = [&](void* p, int which) { View v = c8view(p, H, W, 24, 24, 12 * which); v.c8 = 2; return v; };
+  std::vector<std::string> trunk_rest(kTrunk9.begin() + 1, kTrunk9.end());   // conv2_downsample .. conv9_atrous
+  if (pair1) {
     Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
     c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
-    CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
-    std::vector<std::string> names = with_prefix("", kTrunk9);
-    names.push_back("conv10_atrous");
-    int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, nullptr, nullptr, cat1.p, cat_ld, 0);
+    CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream,
+             opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M));
+    Buf st = c.get(pair_bytes);
+    int rc = run_layer(c, *pair1, stem_view(c, in8.p, H, W), st.p, 24, 0, 2);
     if (rc) return rc;
-  }
-  {
-    Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
-    c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
-    CK(pack8(x2, guide, mask2, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M,
-             opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f, 1, c.stream));
-    std::vector<std::string> names = with_prefix("w", kTrunk9);
-    names.push_back("wconv10_atrous");
+    c.put(in8);
+    std::vector<std::string> na, nb;
+    for (auto& n : trunk_rest) { na.push_back(n); nb.push_back("w" + n); }
+    na.push_back("conv10_atrous"); nb.push_back("wconv10_atrous");
+    rc = run_chain(c, 'G', na, pair_view(st.p, 0), false, Buf(), nullptr, nullptr, cat1.p, cat_ld, 0);
+    if (rc) return rc;
     View v;
     Buf b;
-    int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, &v, &b);
+    rc = run_chain(c, 'G', nb, pair_view(st.p, 1), false, Buf(), &v, &b);
     if (rc) return rc;
+    c.put(st);
     Buf pooled = c.get((size_t)c.B * 96 * 4);
     c.tag("plane_reduce|global style pooling", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
     CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, v.c8, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
@@ -959,6 +974,35 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, cat_ld, 96, tc, c.stream));
     c.put(pooled);
     c.put(b);
+  } else {
+  {
+      Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
+      c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
+      CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
+      std::vector<std::string> names = with_prefix("", kTrunk9);
+      names.push_back("conv10_atrous");
+      int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, nullptr, nullptr, cat1.p, cat_ld, 0);
+      if (rc) return rc;
+    }
+    {
+      Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
+      c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
+      CK(pack8(x2, guide, mask2, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M,
+               opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f, 1, c.stream));
+      std::vector<std::string> names = with_prefix("w", kTrunk9);
+      names.push_back("wconv10_atrous");
+      View v;
+      Buf b;
+      int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, &v, &b);
+      if (rc) return rc;
+      Buf pooled = c.get((size_t)c.B * 96 * 4);
+      c.tag("plane_reduce|global style pooling", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
+      CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, v.c8, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
+      c.tag("broadcast_channels|pooled style vector -> concat blocks", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
+      CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, cat_ld, 96, tc, c.stream));
+      c.put(pooled);
+      c.put(b);
+    }
   }
   Buf xnow = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
   {
@@ -975,7 +1019,18 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   }
   // ---- stage 2: hallucination branch + patch-match branch -> concat -> joint decoder
   Buf cat2 = c.get((size_t)c.B * h * w * 192 * e);
-  {
+  Buf st2;
+  if (pair2) {
+    st2 = c.get(pair_bytes);
+    int rc = run_layer(c, *pair2, stem_view(c, xnow.p, H, W), st2.p, 24, 0, 2);
+    if (rc) return rc;
+    c.put(xnow);
+    std::vector<std::string> nx;
+    for (auto& n : trunk_rest) nx.push_back("x" + n);
+    nx.push_back("xconv10_atrous");
+    rc = run_chain(c, 'G', nx, pair_view(st2.p, 0), false, Buf(), nullptr, nullptr, cat2.p, cat_ld, 0);
+    if (rc) return rc;
+  } else {
     std::vector<std::string> names = with_prefix("x", kTrunk9);
     names.push_back("xconv10_atrous");
     int rc = run_chain(c, 'G', names, stem_view(c, xnow.p, H, W), false, Buf(), nullptr, nullptr, cat2.p, cat_ld, 0);
@@ -984,8 +1039,12 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   {
     View pm;
     Buf pmb;
-    int rc = run_chain(c, 'G', with_prefix("pm", {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}),
-                       stem_view(c, xnow.p, H, W), true, xnow, &pm, &pmb, nullptr, 0, 0, opt[SE_OPT_USE_CAM] ? (tc ? 2 : 0) : -1);   // the layout the attention reads
+    // pmconv6 writes the layout the attention reads: space-to-depth channel-blocked on the tensor-core path, NHWC otherwise
+    const int pm_c8 = opt[SE_OPT_USE_CAM] ? (tc ? 2 : 0) : -1;
+    int rc = pair2 ? run_chain(c, 'G', with_prefix("pm", {"conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}), pair_view(st2.p, 1), true, st2,
+                               &pm, &pmb, nullptr, 0, 0, pm_c8)
+                   : run_chain(c, 'G', with_prefix("pm", {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}),
+                               stem_view(c, xnow.p, H, W), true, xnow, &pm, &pmb, nullptr, 0, 0, pm_c8);
     if (rc) return rc;
     if (opt[SE_OPT_USE_CAM]) {
       Buf ms = c.get((size_t)c.B * h * w * 4);
@@ -1109,6 +1168,44 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
   return fn(c);
 }
 
+// Two 5x5 stems that read the SAME packed 8-channel input become ONE launch with N = 96 (a stem tile is bound by its per-tile
+// protocol and the small-N MMA rate, not by math: one N = 96 launch costs about what one N = 48 launch does).
+//   "G.conv1+wconv1": packed input [x(1-m) (3), sketch, m, x2*m2 (3)]: conv1 reads channels 0..4, wconv1 its own image copy in
+//                     5..7, the sketch channel (weight zeroed under --joint_train_inp, where the reference feeds zeros) and m
+//   "G.xconv1+pmconv1": both read the 3 channels of the blended coarse result
+// Fused output channel order [fA(24) fB(24) | gA(24) gB(24)] so that it is an ordinary gated layer with 96 outputs; the epilogue
+// sends output blocks 0-2 to layer A's space-to-depth tensor and blocks 3-5 to layer B's (EpiParams::blk_split).
+static int make_stem_pair(se_model* m, const char* key, const char* a, const char* b, const int* chan_a, const int* chan_b, float scale_b3) {
+  Layer* A = find_layer(m, 'G', a);
+  Layer* B = find_layer(m, 'G', b);
+  if (!A || !B || !A->set || !B->set) return 0;
+  Layer F;
+  F.name = key;
+  F.spec = Spec{nullptr, 8, 96, 5, 1, 1, false, 0};
+  F.set = true;
+  F.fused_pair = true;
+  F.pair_cin_sum = A->spec.cin + B->spec.cin;
+  F.w_host.assign((size_t)96 * 8 * 25, 0.0f);
+  F.b_host.assign(96, 0.0f);
+  for (int n = 0; n < 96; ++n) {
+    const bool gate = n >= 48;
+    const int r = n % 48;
+    const Layer* S = r < 24 ? A : B;
+    const int* chan = r < 24 ? chan_a : chan_b;
+    const int co = (r % 24) + (gate ? 24 : 0);           // channel of the source layer: features 0..23, gates 24..47
+    F.b_host[n] = S->b_host[co];
+    for (int ci = 0; ci < S->spec.cin; ++ci) {
+      const float sc = (S == B && ci == 3) ? scale_b3 : 1.0f;
+      for (int t = 0; t < 25; ++t) F.w_host[((size_t)n * 8 + chan[ci]) * 25 + t] = S->w_host[((size_t)co * S->spec.cin + ci) * 25 + t] * sc;
+    }
+  }
+  int rc = pack_layer(m, F);
+  if (rc) return rc;
+  F.w_host.clear();
+  m->layers[std::string("G.") + key] = F;
+  return 0;
+}
+
 static int check_hw(int H, int W) {
   SE_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "H and W must be multiples of 8 and >= 16 (two stride-2 convs, 4x4 mask pool, stride-2 patch grid)");
   return 0;
@@ -1163,6 +1260,7 @@ int se_model_set_layer(se_model* m, char net, const char* layer, const float* we
 
 int se_model_set_option(se_model* m, int option, int value) {
   SE_REQUIRE(m && option >= 0 && option < 8, "option");
+  SE_REQUIRE(!m->finalized, "options are fixed at se_model_finalize (they shape the packed weights)");
   m->opt[option] = value;
   return 0;
 }
@@ -1186,8 +1284,18 @@ int se_model_finalize(se_model* m) {
       }
     SE_REQUIRE(nset == 0 || nset == ntot, "layer not set: net" + first_missing);
   }
+  {
+    static const bool no_pairs = getenv("SE_NO_STEM_PAIRS") != nullptr;   // A/B switch for experiments
+    const int id5[5] = {0, 1, 2, 3, 4}, w5[5] = {5, 6, 7, 3, 4}, id3[3] = {0, 1, 2};
+    if (!no_pairs) {
+      int rc = make_stem_pair(m, "conv1+wconv1", "conv1", "wconv1", id5, w5, m->opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f);
+      if (rc) return rc;
+      rc = make_stem_pair(m, "xconv1+pmconv1", "xconv1", "pmconv1", id3, id3, 1.0f);
+      if (rc) return rc;
+    }
+  }
   for (auto& kv : m->layers) {
-    if (!kv.second.set) continue;
+    if (!kv.second.set || kv.second.fused_pair) continue;
     int rc = pack_layer(m, kv.second);
     if (rc) return rc;
     kv.second.w_host.clear();

@@ -25,7 +25,7 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 template <typename T>
 __global__ void pack8_kernel(const float* __restrict__ img, const float* __restrict__ sketch, const float* __restrict__ mask,
                              T* __restrict__ out, int B, int H, int W, int Wp, int padl, int img_mode, float sketch_scale,
-                             int write_mask) {
+                             int write_mask, int img2_mode) {
   // one thread per pixel of the PADDED row (Wp pixels, image at [padl, padl+W)); pads are written as zeros
   const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long HW = (long long)H * W;
@@ -51,7 +51,13 @@ __global__ void pack8_kernel(const float* __restrict__ img, const float* __restr
   for (int c = 0; c < 3; ++c) v[c] = from_f<T>(img[(b * 3 + c) * HW + pix] * a);
   v[3] = from_f<T>((sketch ? sketch[i] : 1.0f) * sketch_scale);   // guide=None -> ones (reference editline_g.py:127-130)
   v[4] = from_f<T>(write_mask ? m : 0.0f);
-  v[5] = v[6] = v[7] = from_f<T>(0.0f);
+  if (img2_mode >= 0) {   // second masked copy of the image in channels 5..7 (the style encoder's input, stem pair conv1 + wconv1)
+    const float a2 = img2_mode == PACK_IMG_ONE ? 1.0f : (img2_mode == PACK_IMG_ONE_MINUS_M ? 1.0f - m : m);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[5 + c] = from_f<T>(img[(b * 3 + c) * HW + pix] * a2);
+  } else {
+    v[5] = v[6] = v[7] = from_f<T>(0.0f);
+  }
   if (sizeof(T) == 2) {
     *reinterpret_cast<uint4*>(out + j * 8) = *reinterpret_cast<const uint4*>(v);   // 8 x bf16 = one 16 B store
   } else {
@@ -61,9 +67,9 @@ __global__ void pack8_kernel(const float* __restrict__ img, const float* __restr
 }
 
 int pack8(const float* img, const float* sketch, const float* mask, void* out, int dt, int B, int H, int W, int Wp, int padl,
-          int img_mode, float sketch_scale, int write_mask, cudaStream_t s) {
+          int img_mode, float sketch_scale, int write_mask, cudaStream_t s, int img2_mode) {
   const long long n = (long long)B * H * Wp;
-  SE_DISPATCH_T(dt, (pack8_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(img, sketch, mask, (T*)out, B, H, W, Wp, padl, img_mode, sketch_scale, write_mask)));
+  SE_DISPATCH_T(dt, (pack8_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(img, sketch, mask, (T*)out, B, H, W, Wp, padl, img_mode, sketch_scale, write_mask, img2_mode)));
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }

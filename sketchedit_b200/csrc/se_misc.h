@@ -9,7 +9,7 @@ enum { HEAD_MASK = 0, HEAD_TANH = 1, HEAD_COARSE = 2, HEAD_FINE = 3 };
 enum { RED_MAX = 0, RED_AVG = 1, RED_RNORM = 2 };
 
 int pack8(const float* img, const float* sketch, const float* mask, void* out, int dt, int B, int H, int W, int Wp, int padl,
-          int img_mode, float sketch_scale, int write_mask, cudaStream_t s);
+          int img_mode, float sketch_scale, int write_mask, cudaStream_t s, int img2_mode = -1);   // img2_mode >= 0: channels 5..7 = img * f(mask)
 int head(const void* x, int dt, int in_c8, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img,
          const float* mask_bin, const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse,
          int Wp, int padl, long long out_bstride, long long msoft_bstride, unsigned char* out_u8,

@@ -373,7 +373,7 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     // the block group, so the consumer's taps become plain stride-1 reads of one parity each
     const uint32_t Hs = e.Hout >> 1, Ws = e.Wout >> 1, par = ((oy & 1) << 1) | (ox & 1);
     ostep = Hs * Ws;
-    obase = (((uint32_t)img * e.ldo + par * (e.ldo >> 2) + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws + (ox >> 1);
+    obase = (((uint32_t)img * e.ldo + par * (uint32_t)e.par_stride + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws + (ox >> 1);
   } else if (e.out_c8) {
     ostep = (uint32_t)e.Hout * e.Wout;
     obase = (((uint32_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout + ox;
@@ -381,6 +381,8 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     ostep = 1;
     obase = (((uint32_t)img * e.Hout + oy) * e.Wout + ox) * (e.ldo >> 3) + (e.choff >> 3);
   }
+  // offset of output block b (fused layer pairs: the second layer's blocks sit blk_jump further on)
+  auto boff = [&](int b) -> uint32_t { return obase + (uint32_t)b * ostep + (b >= e.blk_split ? (uint32_t)e.blk_jump : 0u); };
   // 4 outputs [c, c+4) from f[k..k+3], g[k..k+3]
   auto gate4 = [&](float* f, const float* g, int c, int k) {
     const float4 b = lds128(cs0 + c * 4), bl = lds128(cs0 + (cst_n + c) * 4), hb = lds128(cs0 + (2 * cst_n + goff + c) * 4);
@@ -398,9 +400,8 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     if (valid) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) gate4(f, g, c0 + 4 * q, 4 * q);
-      const uint32_t o = obase + (uint32_t)b * ostep;
-      ybase[o] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      ybase[o + ostep] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+      ybase[boff(b)] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      ybase[boff(b + 1)] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
     }
   };
   auto do8 = [&](int b) {
@@ -412,7 +413,7 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     if (valid) {
       gate4(f, g, c0, 0);
       gate4(f, g, c0 + 4, 4);
-      ybase[obase + (uint32_t)b * ostep] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      ybase[boff(b)] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
   };
   if (nsplit == 1) {
@@ -437,7 +438,7 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
         const int bb = grp + j * nsplit;
         gate4(f[j], g[j], bb * 8, 0);
         gate4(f[j], g[j], bb * 8 + 4, 4);
-        ybase[obase + (uint32_t)bb * ostep] =
+        ybase[boff(bb)] =
             make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]), pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
       }
     }
@@ -459,7 +460,7 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
   if (e.out_c8 == 2) {
     const uint32_t Hs = e.Hout >> 1, Ws = e.Wout >> 1, par = ((oy & 1) << 1) | (ox & 1);
     ostep = Hs * Ws;
-    obase = (((uint32_t)img * e.ldo + par * (e.ldo >> 2) + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws + (ox >> 1);
+    obase = (((uint32_t)img * e.ldo + par * (uint32_t)e.par_stride + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws + (ox >> 1);
   } else if (e.out_c8) {
     ostep = (uint32_t)e.Hout * e.Wout;
     obase = (((uint32_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout + ox;
