@@ -12,7 +12,7 @@
 #   all[:ARGS]          light ncu capture (speed-of-light, memory, tensor pipe, DRAM bytes) of EVERY launch of one forward
 #                                                                    -> gpurun_out/all_<ARGS>.ncu-rep (tools/ncu_summary.py)
 #   probe[:CASES]       SE_TC_DEBUG role timers of single layers (tools/tc_probe.py)
-#   env:K=V             export K=V for the following steps
+#   env:K=V / unset:K   export K=V / unset K for the following steps
 #
 #   gpurun -- 'bash tools/gpu.sh tests bench bench:--size,512 launches:--batch,32'
 mkdir -p gpurun_out
@@ -22,6 +22,7 @@ for step in "$@"; do
   echo "=================== $step"
   case $kind in
     env) export "$rest" ;;
+    unset) unset "$rest" ;;
     tests)
       if [ -n "$rest" ]; then K=(-k "$rest"); else K=(); fi
       timeout 1500 python -m pytest tests -q -m gpu --timeout 900 "${K[@]}" > gpurun_out/pytest_gpu.log 2>&1; tail -${TAIL:-40} gpurun_out/pytest_gpu.log ;;
