@@ -23,7 +23,10 @@ typedef struct se_model se_model;
 enum {
   SE_PREC_BF16_TC = 0,     /* bf16 activations + weights, tcgen05 tensor-core kernels, fp32 accumulation */
   SE_PREC_FP32_EXACT = 1,  /* fp32 activations + weights, CUDA-core fp32 FMA kernels (fp32 parity config) */
-  SE_PREC_BF16_DIRECT = 2  /* bf16 activations, CUDA-core kernels (cross-check of the tcgen05 path) */
+  SE_PREC_BF16_DIRECT = 2, /* bf16 activations, CUDA-core kernels (cross-check of the tcgen05 path) */
+  SE_PREC_FP32_TC = 3      /* fp32-parity arithmetic ON the tensor cores: activations and weights as fp16 hi + fp16 lo pairs (22
+                              significant bits), three tcgen05 products per tap (hi*hi + hi*lo + lo*hi), fp32 accumulation and exact-math
+                              epilogue. The fp32 parity config (1e-3) runs here; SE_PREC_FP32_EXACT stays as its cross-check. */
 };
 
 /* model options == the reference's command-line flags read on the hot path

@@ -15,8 +15,9 @@ class EditLine2Model(torch.nn.Module):
     @staticmethod
     def modify_commandline_options(parser, is_train):
         networks.modify_commandline_options(parser, is_train)
-        parser.add_argument("--precision", default="bf16", choices=("bf16", "fp32"),
-                            help="B200 arithmetic: bf16 tensor-core path or fp32 CUDA-core parity path")
+        parser.add_argument("--precision", default="bf16", choices=("bf16", "fp32", "fp32_direct"),
+                            help="B200 arithmetic: bf16 tensor-core path, fp32-parity arithmetic on the tensor cores (split-half fp16), "
+                                 "or its fp32 CUDA-core cross-check")
         return parser
 
     def __init__(self, opt):

@@ -76,5 +76,6 @@ def check(rc):
         raise SketchEditB200Error("sketchedit_b200 call failed (rc=%d): %s" % (rc, msg.decode() if msg else "?"))
 
 
-PREC = {"bf16": 0, "fp32": 1, "bf16_direct": 2}
+# "fp32": fp32-parity arithmetic on the tensor cores (split-half fp16, SE_PREC_FP32_TC); "fp32_direct": the fp32 CUDA-core kernels
+PREC = {"bf16": 0, "fp32": 3, "fp32_direct": 1, "bf16_direct": 2}
 OPT = {"use_cam": 0, "pool_avg": 1, "no_mask_cc": 2, "no_mask_coarse": 3, "joint_train_inp": 4}

@@ -40,7 +40,7 @@ const char* last_error();
 constexpr int TILE_H = 8;
 constexpr int TILE_W = 16;
 constexpr int TILE_M = TILE_H * TILE_W;  // 128 = UMMA M = TMEM lanes
-constexpr int MAX_TAPS = 32;
+constexpr int MAX_TAPS = 64;              // 9 taps x 3 operand-split products (+ space-to-depth / deconv variants)
 constexpr int KCHUNK = 32;               // bf16 elements per K chunk = 64 B = SWIZZLE_64B span
 
 enum Epilogue : int {
@@ -49,7 +49,11 @@ enum Epilogue : int {
   EPI_LINEAR = 2,     // (y[c] + bias[c]) * scale * colscale[n][c]       (raw conv / attention GEMMs)
 };
 
-enum DType : int { DT_BF16 = 0, DT_F32 = 1 };
+enum DType : int { DT_BF16 = 0, DT_F32 = 1, DT_F16X2 = 2 };
+// DT_F16X2: "split half" storage of an fp32 tensor for the fp32-on-tensor-cores mode: value = hi + lo with hi = fp16(v),
+// lo = fp16(v - hi) (22 significant bits). A channel-blocked tensor keeps the hi blocks first and the lo blocks `CB` blocks
+// further on ([N][2*CB][H][W][8]; space-to-depth: per parity group). A convolution then is three tcgen05 products per tap,
+// x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (the dropped lo*lo term is 2^-22 relative), accumulated in fp32.
 
 // One generalised convolution launch. Positions p=(py,px) on an Ho x Wo grid; input pixel for tap t
 // is (py*stride + dy[t], px*stride + dx[t]) (zero outside the image); output pixel is
@@ -81,6 +85,8 @@ struct ConvParams {
   int Hout, Wout, ldo, choff;
   int osy, ooy, osx, oox;
   int out_blk_split, out_blk_jump, out_par_stride;   // fused layer pairs (EpiParams::blk_split ..); 0 = plain layer
+  int f16x2;                    // split-half mode (DT_F16X2): fp16 operands, split-half output, exact-math epilogue
+  long long out_split_stride;   // f16x2: 16 B units between the hi and the lo part of an output block
   // epilogue
   int epi;
   float scale;                  // EPI_LINEAR
@@ -102,6 +108,7 @@ struct EpiParams {
   // layer's tensor, blk_jump (16 B units) further on; par_stride = channel blocks between the parity groups of a
   // space-to-depth output (ldo / 4 unless two such tensors share the buffer). blk_split = 1 << 20: off.
   int blk_split, blk_jump, par_stride;
+  int nsplit, split_stride;   // nsplit = 2: split-half output (DT_F16X2): the lo part of every block is stored split_stride (16 B units) further on
   int has_bias;   // 0: the launch has no bias vector (attention GEMMs): no per-column constants are staged in shared memory
   int goff;   // gated epilogues: accumulator column of gate channel 0 (= Cout/2 rounded up to 8; the weight image
               // places feature c at column c and its gate at goff + c, columns in between are zero weights)

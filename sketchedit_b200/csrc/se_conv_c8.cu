@@ -202,12 +202,12 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
               if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
               tma_load_2d_pair(st + stage_a, &tmB, lead_bar, 0, (ks * 2 + (int)cta_rank) * (b_bytes >> 9));   // 512 B rows
-              if (!halo) tma_load_4d_pair(st, &tmA, lead_bar, (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off, img);
+              if (!halo) tma_load_4d_pair(st, &tmA, lead_bar, (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off + p.tap_cb[ks], img);
             } else {
               mbar_expect_tx(&full_bar[stage], (uint32_t)((halo ? 0 : p.a_tx_bytes) + stage_b));
               if (!p.resident) bulk_load_1d(st + stage_a, p.w + (size_t)ks * b_bytes, (uint32_t)b_bytes, &full_bar[stage]);
               if (!halo) {   // PERTAP: a stage is exactly one tap
-                tma_load_4d(st, &tmA, &full_bar[stage], (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off, img);
+                tma_load_4d(st, &tmA, &full_bar[stage], (x0 + p.dx[ks]) * 8, y0 + p.dy[ks], p.x_cb_off + p.tap_cb[ks], img);
               }
             }
           }
@@ -228,7 +228,8 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ahead, and mbarrier parity waits alias modulo 2 (a 3-issuer experiment corrupted tiles and hung exactly so).
     const int n_issuers = (!staged && (p.a_bufs & 1) == 0 && (acc_stages & 1) == 0) ? 2 : 1;
     const int me = (warp == 3) ? 1 : 0;   // a second issuer that is not needed simply finds no tile below
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
+    // D = f32; A, B = bf16 (format 1) or fp16 (format 0, split-half mode), both K-major; N = NT; M = 128 / 256
+    const uint32_t idesc = (1u << 4) | (p.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     long long t_wfull = 0, t_wtmem = 0, t_whalo = 0, t_begin = clock64();
@@ -410,7 +411,10 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = (py < p.Ho) && (px < p.Wo);
       // output pixel of this position (sub-pixel classes: osy = osx = 2 and a per-class offset)
       const int oy = py * p.e.osy + (NCLS > 1 ? p.cls_ooy[cls] : p.e.ooy), ox = px * p.e.osx + (NCLS > 1 ? p.cls_oox[cls] : p.e.oox);
-      if (KS1 && p.ecst_nb) {   // (only the single-k-step instantiations carry this code: the launcher sets ecst_nb for them alone)
+      if (p.e.nsplit > 1) {     // split-half output (fp32-on-tensor-cores mode): exact-math gate, hi / lo stores
+        if (p.e.epi == EPI_GATE_ELU) tc_epilogue_gated_split<true>(p.e, bias_s, cst_n, taddr, img, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
+        else tc_epilogue_gated_split<false>(p.e, bias_s, cst_n, taddr, img, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
+      } else if (KS1 && p.ecst_nb) {   // (only the single-k-step instantiations carry this code: the launcher sets ecst_nb for them alone)
         // constants as kernel parameters (gated, bf16 block output, 2 or 3 blocks, one group per tile)
         const bool elu = (p.e.epi == EPI_GATE_ELU);
         if (p.ecst_nb == 3) { if (elu) tc_epilogue_gated_const<true, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); else tc_epilogue_gated_const<false, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); }
@@ -497,6 +501,7 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
     L->HR = HR; L->WR = WR; L->pad_y0 = -mn_y; L->pad_x0 = -mn_x;
   } else {
     L->HR = C8_TH; L->WR = C8_TW; L->pad_y0 = 0; L->pad_x0 = 0;
+    L->cb_in = (w.n64 * 64 + w.n32 * 32) / 8;   // a box per tap, starting at the tap's own channel block (C8Params::tap_cb)
   }
   L->a_tx_bytes = L->cb_in * L->HR * L->WR * 16;
   L->a_bytes = (L->a_tx_bytes + 1023) / 1024 * 1024;
@@ -662,14 +667,17 @@ bool c8_pair_capable(const C8Layer& L) {
 int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, const C8Group* grp) {
   const C8Layer& L = grp ? grp->geo : L_in;
   const TcWeights& w = L.w;
-  SE_REQUIRE(c.in_dt == DT_BF16 && c.in_c8 == 1, "conv_c8 reads bf16 channel-blocked activations");
+  SE_REQUIRE((c.in_dt == DT_BF16 || c.in_dt == DT_F16X2) && c.in_c8 == 1, "conv_c8 reads 16-bit channel-blocked activations");
+  SE_REQUIRE((c.in_dt == DT_F16X2) == (c.f16x2 != 0) && (c.out_dt == DT_F16X2) == (c.f16x2 != 0), "split-half mode: both sides");
   SE_REQUIRE(c.stride == 1, "conv_c8 handles stride-1 convolutions");
   SE_REQUIRE((reinterpret_cast<uintptr_t>(c.x) & 127) == 0, "input base must be 128 B aligned");
   SE_REQUIRE(c.ntaps == w.ntaps && c.ntaps <= MAX_TAPS, "tap count mismatch");
-  for (int t = 0; t < c.ntaps && !grp; ++t) SE_REQUIRE(c.tap_cb[t] == L.tap_cb[t] && (L.tap_cb[t] == 0 || L.mode == C8_HALO), "per-tap channel blocks need the halo mode");
+  for (int t = 0; t < c.ntaps && !grp; ++t) SE_REQUIRE(c.tap_cb[t] == L.tap_cb[t], "per-tap channel blocks differ from the packed layer");
   SE_REQUIRE(c.Wi * 8 <= (1 << 30) && L.WR * 8 <= 256 && L.HR <= 256 && L.cb_in <= 256, "TMA box limits");
   C8Params p;
   memset(&p, 0, sizeof(p));
+  p.f16 = c.f16x2 ? 1 : 0;
+  for (int t = 0; t < c.ntaps; ++t) p.tap_cb[t] = L.tap_cb[t];
   p.N = c.N; p.Ho = c.Ho; p.Wo = c.Wo;
   p.tiles_x = (c.Wo + C8_TW - 1) / C8_TW;
   p.tiles_y = (c.Ho + C8_TH - 1) / C8_TH;
@@ -692,14 +700,14 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
   p.sbo_bytes = L.WR * 16;
   p.bias = c.bias;
   fill_epi(c, w.NT, &p.e);
-  SE_REQUIRE(c.out_dt != DT_BF16 || epi_addressable(c), "output tensor too large / misaligned for 32-bit block addressing");
+  SE_REQUIRE(c.out_dt == DT_F32 || epi_addressable(c), "output tensor too large / misaligned for 32-bit block addressing");
   {
     // epilogue constants as kernel parameters when the tile is drained by one group and has 2 or 3 blocks (N <= 48: the
     // 256^2 / 128^2 layers; with 6 blocks the two-pass form measured slower than the shared-memory constants)
     static const bool no_ecst = getenv("SE_C8_NOECST") != nullptr;   // A/B switch for experiments
     const int half = c.Cout / 2, nb = (half + 7) / 8;
     p.ecst_nb = 0;
-    if (!no_ecst && c.epi != EPI_LINEAR && c.bias_host != nullptr && epi_fast_ok(p.e) && w.NT <= 128 && (nb == 2 || nb == 3) &&
+    if (!no_ecst && !c.f16x2 && c.epi != EPI_LINEAR && c.bias_host != nullptr && epi_fast_ok(p.e) && w.NT <= 128 && (nb == 2 || nb == 3) &&
         tc_ksteps(w) == 1 && L.resident && L.mode == C8_HALO) {
       p.ecst_nb = nb;
       for (int i = 0; i < 24; ++i) {
@@ -721,14 +729,15 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
       for (int u = 0; u < n_u64 + n_u32; ++u) {
         const bool is64 = u < n_u64;
         const int t = is64 ? u / w.n64 : u - n_u64;
-        const int cb0 = L.tap_cb[t] + (is64 ? (u - t * w.n64) * 8 : w.n64 * 8);
+        const int cb0 = (halo ? L.tap_cb[t] : 0) + (is64 ? (u - t * w.n64) * 8 : w.n64 * 8);   // PERTAP: the box starts at the tap's block
         const int tdy = grp ? grp->dy[k][t] : c.dy[t], tdx = grp ? grp->dx[k][t] : c.dx[t];
         const int oy = halo ? tdy + L.pad_y0 : 0, ox = halo ? tdx + L.pad_x0 : 0;
         p.aoff[k * C8_CLS_UNITS + u] = (uint32_t)((cb0 * L.HR + oy) * L.WR + ox) * 16u;
       }
   }
-  SE_REQUIRE(c.epi == EPI_LINEAR || (c.Cout % 2 == 0 && c.out_dt == DT_BF16), "gated epilogue needs even Cout, bf16 out");
-  SE_REQUIRE(!c.out_c8 || (c.out_dt == DT_BF16 && c.choff % 8 == 0), "C8 output must be bf16 with a channel offset multiple of 8");
+  SE_REQUIRE(c.epi == EPI_LINEAR || (c.Cout % 2 == 0 && (c.out_dt == DT_BF16 || c.out_dt == DT_F16X2)), "gated epilogue needs even Cout, 16-bit out");
+  SE_REQUIRE(!c.out_c8 || ((c.out_dt == DT_BF16 || c.out_dt == DT_F16X2) && c.choff % 8 == 0), "C8 output must be 16-bit with a channel offset multiple of 8");
+  SE_REQUIRE(!c.f16x2 || (c.out_c8 != 0 && c.epi != EPI_LINEAR), "split-half output is channel-blocked and gated");
   SE_REQUIRE(c.out_c8 != 2 || (c.epi != EPI_LINEAR && c.Hout % 2 == 0 && c.Wout % 2 == 0 && c.ldo % 4 == 0 && (c.Cout / 2) % 8 == 0),
              "space-to-depth output: gated layer, even size, whole channel blocks");
 

@@ -7,7 +7,7 @@ namespace se {
 
 enum { C8_HALO = 0, C8_PERTAP = 1 };
 constexpr int C8_MAX_ABUFS = 8;   // halo ring depth (resident layers)
-constexpr int C8_MAX_UNITS = 64;   // (tap, channel chunk) K units per tile
+constexpr int C8_MAX_UNITS = 128;   // (tap, channel chunk) K units per tile (split-half layers: 3 products per tap)
 
 // per-layer (per sub-pixel class) configuration fixed at weight-packing time
 struct C8Layer {
@@ -59,6 +59,8 @@ struct C8Params {
   // constant-bank operands of the FMAs (no shared-memory loads in the epilogue). ecst_nb = 8-column blocks, 0 = unused
   int ecst_nb;
   float ecst[3][24];
+  int f16;                        // operands are fp16 (split-half mode) instead of bf16
+  int8_t tap_cb[MAX_TAPS];        // PERTAP mode: first channel block of each tap's box (split-half / space-to-depth inputs)
   int ncls, cls_bytes;            // fused deconv classes (C8Group): classes per tile, bytes between their weight images
   int cls_ooy[C8_MAX_CLS], cls_oox[C8_MAX_CLS];
   unsigned long long* dbg;

@@ -294,6 +294,8 @@ void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
   e->blk_split = c.out_blk_split > 0 ? c.out_blk_split : (1 << 20);
   e->blk_jump = c.out_blk_split > 0 ? c.out_blk_jump : 0;
   e->par_stride = c.out_par_stride > 0 ? c.out_par_stride : (c.ldo >> 2);
+  e->nsplit = c.f16x2 ? 2 : 1;
+  e->split_stride = (int)c.out_split_stride;
   e->goff = (c.epi == EPI_LINEAR) ? 0 : gated_goff(c.Cout);
 }
 // the fast epilogue addresses the output in 32-bit units of 16 B

@@ -5,6 +5,9 @@
 //   EditLine2Model inference       reference models/editline2_model.py:128-133,338-370
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -176,6 +179,12 @@ struct ClassW {
   bool s2d = false;
   int8_t c8dy[MAX_TAPS], c8dx[MAX_TAPS], c8cb[MAX_TAPS];
   int osy = 1, ooy = 0, osx = 1, oox = 0;
+  // split-half twin (SE_PREC_FP32_TC, DT_F16X2): every tap becomes three virtual taps (x_hi, w_hi), (x_hi, w_lo), (x_lo, w_hi); a
+  // virtual tap reads the hi or lo channel blocks of the input (s_cb) and its weight image holds fp16(w) or fp16(w - fp16(w))
+  C8Layer c8s;
+  bool has_split = false;
+  int s_ntaps = 0;
+  int8_t s_dy[MAX_TAPS], s_dx[MAX_TAPS], s_cb[MAX_TAPS];
 };
 
 struct Layer {
@@ -307,52 +316,68 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
       tc_choose_stage(&tc);
       tcp = &tc;
     }
-    TcWeights& tc = *tcp;
-    // the exact (swizzled) shared-memory image of every pipeline stage, see se_conv_tc.h
-    const int ksteps = tc_ksteps(tc), sb = tc_stage_b_bytes(tc);
-    std::vector<uint16_t> img((size_t)ksteps * sb / 2, 0);
-    // gate channels (n >= Cout/2) are stored pre-multiplied by 0.5 (exact in bf16): the accumulator then holds 0.5*g and
-    // the epilogue's sigmoid(g + b) = 0.5*tanh(0.5*g + 0.5*b) + 0.5 needs one add (with a constant operand) before the MUFU
-    auto wv = [&](int t, int ci, int n) -> uint16_t {
-      return ci < Ci ? f32_to_bf16_rn(weff[((size_t)t * Ci + ci) * Cout + n] * (n >= Cout / 2 ? 0.5f : 1.0f)) : (uint16_t)0;
+    // the exact (swizzled) shared-memory image of every pipeline stage, see se_conv_tc.h. Gate channels (n >= Cout/2) are stored
+    // pre-multiplied by 0.5 (exact): the accumulator then holds 0.5*g and the epilogue's sigmoid(g + b) = 0.5*tanh(0.5*g + 0.5*b) + 0.5
+    // needs one add (with a constant operand) before the MUFU
+    auto build_images = [&](TcWeights& tc, C8Layer* c8, const std::function<uint16_t(int, int, int)>& wv) -> int {
+      const int ksteps = tc_ksteps(tc), sb = tc_stage_b_bytes(tc);
+      std::vector<uint16_t> img((size_t)ksteps * sb / 2, 0);
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool pair = pass == 1;
+        if (pair && !(c8 && c8_pair_capable(*c8))) break;
+        // pass 1: second copy in CTA-pair format (se_conv_c8.cu, PAIR = 1): each CTA of a pair streams only its half of the rows
+        std::fill(img.begin(), img.end(), (uint16_t)0);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          uint16_t* base = img.data() + (size_t)ks * sb / 2;
+          for (int j = 0; j < tc.r64 && tc.n64; ++j) {
+            const int u = ks * tc.r64 + j, t = u / tc.n64, chunk = u % tc.n64;
+            for (int n = 0; n < Cout; ++n)
+              for (int k = 0; k < 64; ++k) {
+                const uint32_t off = pair ? c8_pair_image_offset(tc, true, j, gated_column(Cout, n), k) : tc_b_image_offset(tc.NT, tc.r64, true, j, gated_column(Cout, n), k);
+                base[off / 2] = wv(t, chunk * 64 + k, n);
+              }
+          }
+          for (int j = 0; j < tc.r32 && tc.n32; ++j) {
+            const int t = ks * tc.r32 + j;
+            for (int n = 0; n < Cout; ++n)
+              for (int k = 0; k < 32; ++k) {
+                const uint32_t off = pair ? c8_pair_image_offset(tc, false, j, gated_column(Cout, n), k)
+                                          : tc_b_image_offset(tc.NT, tc.n64 ? tc.r64 : 0, false, j, gated_column(Cout, n), k);
+                base[off / 2] = wv(t, tc.n64 * 64 + k, n);
+              }
+          }
+        }
+        void* d = nullptr;
+        int rc = upload(m, img.data(), img.size() * 2, &d);
+        if (rc) return rc;
+        if (pair) c8->w_pair = d; else tc.data = d;
+      }
+      return 0;
     };
-    for (int ks = 0; ks < ksteps; ++ks) {
-      uint16_t* base = img.data() + (size_t)ks * sb / 2;
-      for (int j = 0; j < tc.r64 && tc.n64; ++j) {
-        const int u = ks * tc.r64 + j, t = u / tc.n64, chunk = u % tc.n64;
-        for (int n = 0; n < Cout; ++n)
-          for (int k = 0; k < 64; ++k) base[tc_b_image_offset(tc.NT, tc.r64, true, j, gated_column(Cout, n), k) / 2] = wv(t, chunk * 64 + k, n);
-      }
-      for (int j = 0; j < tc.r32 && tc.n32; ++j) {
-        const int t = ks * tc.r32 + j;
-        for (int n = 0; n < Cout; ++n)
-          for (int k = 0; k < 32; ++k) base[tc_b_image_offset(tc.NT, tc.n64 ? tc.r64 : 0, false, j, gated_column(Cout, n), k) / 2] = wv(t, tc.n64 * 64 + k, n);
-      }
-    }
-    void* d = nullptr;
-    int rc = upload(m, img.data(), img.size() * 2, &d);
+    auto wval = [&](int t, int ci, int n) -> float { return ci < Ci ? weff[((size_t)t * Ci + ci) * Cout + n] * (n >= Cout / 2 ? 0.5f : 1.0f) : 0.0f; };
+    int rc = build_images(*tcp, cw.use_c8 ? &cw.c8 : nullptr, [&](int t, int ci, int n) -> uint16_t { return f32_to_bf16_rn(wval(t, ci, n)); });
     if (rc) return rc;
-    tc.data = d;
-    if (cw.use_c8 && c8_pair_capable(cw.c8)) {
-      // second copy in CTA-pair format (se_conv_c8.cu, PAIR = 1): each CTA of a pair streams only its half of the rows
-      std::fill(img.begin(), img.end(), (uint16_t)0);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        uint16_t* base = img.data() + (size_t)ks * sb / 2;
-        for (int j = 0; j < tc.r64 && tc.n64; ++j) {
-          const int u = ks * tc.r64 + j, t = u / tc.n64, chunk = u % tc.n64;
-          for (int n = 0; n < Cout; ++n)
-            for (int k = 0; k < 64; ++k) base[c8_pair_image_offset(tc, true, j, gated_column(Cout, n), k) / 2] = wv(t, chunk * 64 + k, n);
+    if (cw.use_c8) {
+      // ---- split-half twin: virtual tap 3t + p, p = 0: (x_hi, w_hi), 1: (x_hi, w_lo), 2: (x_lo, w_hi)
+      const int CB = L.is_stem ? 1 : Ci / 8;   // channel blocks of one half of the input (the packed stem input is one block)
+      cw.s_ntaps = 3 * cw.ntaps;
+      SE_REQUIRE(cw.s_ntaps <= MAX_TAPS, "too many virtual taps");
+      for (int t = 0; t < cw.ntaps; ++t)
+        for (int pp = 0; pp < 3; ++pp) {
+          cw.s_dy[3 * t + pp] = cw.c8dy[t];
+          cw.s_dx[3 * t + pp] = cw.c8dx[t];
+          cw.s_cb[3 * t + pp] = (int8_t)(2 * cw.c8cb[t] + (pp == 2 ? CB : 0));   // a parity group holds 2 * CB blocks
         }
-        for (int j = 0; j < tc.r32 && tc.n32; ++j) {
-          const int t = ks * tc.r32 + j;
-          for (int n = 0; n < Cout; ++n)
-            for (int k = 0; k < 32; ++k) base[c8_pair_image_offset(tc, false, j, gated_column(Cout, n), k) / 2] = wv(t, tc.n64 * 64 + k, n);
-        }
-      }
-      void* dp = nullptr;
-      rc = upload(m, img.data(), img.size() * 2, &dp);
+      rc = c8_configure(&cw.c8s, cw.s_ntaps, cw.s_dy, cw.s_dx, Ci, Cout, L.is_stem, cw.s_cb);
       if (rc) return rc;
-      cw.c8.w_pair = dp;
+      auto half_bits = [](float v) -> uint16_t { return __half_as_ushort(__float2half_rn(v)); };
+      rc = build_images(cw.c8s.w, &cw.c8s, [&](int vt, int ci, int n) -> uint16_t {
+        const float w = wval(vt / 3, ci, n);
+        const float hi = __half2float(__float2half_rn(w));
+        return (vt % 3) == 1 ? half_bits(w - hi) : half_bits(w);
+      });
+      if (rc) return rc;
+      cw.has_split = true;
     }
   }
   return 0;
@@ -525,8 +550,11 @@ struct Ctx {
     if (!g_timing || dry) return;
     tag_.name = name; tag_.tensor = tensor; tag_.flops_alg = flops_alg; tag_.flops_exec = flops_exec; tag_.bytes_alg = bytes_alg; tag_.set = true;
   }
-  int act_dt() const { return prec == SE_PREC_FP32_EXACT ? DT_F32 : DT_BF16; }
-  size_t esz() const { return prec == SE_PREC_FP32_EXACT ? 4 : 2; }
+  bool tc() const { return prec == SE_PREC_BF16_TC || prec == SE_PREC_FP32_TC; }   // tcgen05 kernels over channel-blocked activations
+  bool split() const { return prec == SE_PREC_FP32_TC; }                            // ... in split-half storage (DT_F16X2)
+  int sp() const { return split() ? 2 : 1; }                                        // channel-block multiplier of that storage
+  int act_dt() const { return prec == SE_PREC_FP32_EXACT ? DT_F32 : (split() ? DT_F16X2 : DT_BF16); }
+  size_t esz() const { return (prec == SE_PREC_FP32_EXACT || split()) ? 4 : 2; }
   Buf get(size_t bytes) { Buf b; b.bytes = bytes; b.p = arena.alloc(bytes); return b; }
   void put(Buf& b) { if (b.p) arena.release(b.p, b.bytes); b.p = nullptr; }
 };
@@ -567,6 +595,7 @@ static Layer* find_ready(se_model* m, char net, const std::string& name) {
 }
 
 static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw) {
+  if (c.split() && cw.has_split) return c8_launch(cp, cw.c8s, c.stream);
   if (c.prec == SE_PREC_BF16_TC && cw.has_tc) return cw.use_c8 ? c8_launch(cp, cw.c8, c.stream) : tc_launch(cp, cw.tc, c.stream);
   ConvParams d = cp;
   d.w = cw.w_direct;
@@ -577,17 +606,17 @@ static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw) {
 // layout a layer wants for its input on the bf16 tensor-core path (stride-2 layers read NHWC, the rest C8)
 // 0 NHWC, 1 channel-blocked (C8), 2 channel-blocked space-to-depth (stride-2 layers)
 static int wants_c8(const Ctx& c, const Layer& L) {
-  if (c.prec != SE_PREC_BF16_TC || L.is_head) return 0;
+  if (!c.tc() || L.is_head) return 0;
   if (L.spec.stride == 1) return 1;
   return (!L.cls.empty() && L.cls[0].s2d) ? 2 : 0;
 }
 static inline size_t act_bytes(const Ctx& c, int H, int W, int C, int c8) {
-  return c8 ? (size_t)c.B * ((C + 7) / 8) * H * W * 16 : (size_t)c.B * H * W * C * c.esz();
+  return c8 ? (size_t)c.B * ((C + 7) / 8) * H * W * 16 * c.sp() : (size_t)c.B * H * W * C * c.esz();
 }
 // the packed 8-channel network input (zero-padded rows of stem_wp(W) pixels): NHWC with C = ld = 8 for the CUDA-core
 // kernels, the same bytes seen as one channel block of width stem_wp(W) for the tensor-core path
 static View stem_view(const Ctx& c, void* p, int H, int W) {
-  if (c.prec == SE_PREC_BF16_TC) return c8view(p, H, W, 8, 1, 0);
+  if (c.tc()) return c8view(p, H, W, 8, c.sp(), 0);
   return nhwc(p, H, W, 8, 8);
 }
 
@@ -597,6 +626,7 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
   const int Ho = s.deconv ? in.H : (in.H + s.stride - 1) / s.stride;   // position grid
   const int Wo = s.deconv ? in.W : (in.W + s.stride - 1) / s.stride;
   const bool fused = c.prec == SE_PREC_BF16_TC && !L.groups.empty() && in.c8 == 1;
+  const bool split = c.split();
   const int n_launch = fused ? (int)L.groups.size() : (int)L.cls.size();
   for (int li = 0; li < n_launch; ++li) {
     const C8Group* grp = fused ? &L.groups[li] : nullptr;
@@ -620,12 +650,24 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     cp.ntaps = cw.ntaps;
     memcpy(cp.dy, cw.dy, sizeof(cp.dy));
     memcpy(cp.dx, cw.dx, sizeof(cp.dx));
+    if (split) {
+      SE_REQUIRE(cw.has_split && in.c8 && out_c8, "split-half mode runs on channel-blocked activations (layer " + L.name + ")");
+      cp.f16x2 = 1;
+      // hi blocks first, lo blocks after them: per image (channel-blocked) or per parity group (space-to-depth)
+      cp.out_split_stride = out_c8 == 2 ? (long long)(ldo / 8) * (Ho * cw.osy / 2) * (Wo * cw.osx / 2) : (long long)(ldo / 2) * (Ho * cw.osy) * (Wo * cw.osx);
+    }
     if (in.c8 == 2) {   // space-to-depth input: a stride-1 problem on the half-resolution grid with per-tap parity blocks
       SE_REQUIRE(cw.s2d && in.H % 2 == 0 && in.W % 2 == 0, "space-to-depth input at layer " + L.name);
       cp.Hi = in.H / 2; cp.Wi = in.W / 2; cp.stride = 1;
       memcpy(cp.dy, cw.c8dy, sizeof(cp.dy));
       memcpy(cp.dx, cw.c8dx, sizeof(cp.dx));
       memcpy(cp.tap_cb, cw.c8cb, sizeof(cp.tap_cb));
+    }
+    if (split) {        // the virtual taps of the split-half twin (already in space-to-depth form where that applies)
+      cp.ntaps = cw.s_ntaps;
+      memcpy(cp.dy, cw.s_dy, sizeof(cp.dy));
+      memcpy(cp.dx, cw.s_dx, sizeof(cp.dx));
+      memcpy(cp.tap_cb, cw.s_cb, sizeof(cp.tap_cb));
     }
     cp.w = nullptr; cp.w_img_stride = 0;
     cp.bias = L.bias; cp.bias_host = L.b_host.data(); cp.Cout = s.cout;
@@ -648,11 +690,11 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
       const double pos = (double)c.B * Ho * Wo * gc, ncls = (double)L.cls.size() / gc;
       const double cin_alg = L.fused_pair ? L.pair_cin_sum / 2.0 : (double)s.cin;   // a stem pair: two 48-output layers over their own channels
       const double f_alg = 2.0 * pos * s.cout * cin_alg * (s.deconv ? 9.0 : (double)s.k * s.k);
-      const double f_exec = 2.0 * pos * s.cout * cin_alg * (s.deconv ? 4.0 : (double)s.k * s.k);
+      const double f_exec = 2.0 * pos * s.cout * cin_alg * (s.deconv ? 4.0 : (double)s.k * s.k) * (split ? 3.0 : 1.0);   // split-half: 3 products per tap
       const double bytes = ((double)c.B * in.H * in.W * (L.fused_pair ? 8.0 : (double)s.cin) / ncls + pos * (s.cout / 2) + (double)s.cout * s.cin * s.k * s.k / ncls) * c.esz();
-      const bool tcp = c.prec == SE_PREC_BF16_TC && cw.has_tc;
+      const bool tcp = c.tc() && cw.has_tc;
       char buf[160];
-      snprintf(buf, sizeof(buf), "%s|%s %d->%d k%d s%d d%d @%dx%d", tcp ? (cw.use_c8 ? "conv_c8_kernel" : "conv_tc_kernel") : "conv_direct_kernel",
+      snprintf(buf, sizeof(buf), "%s|%s %d->%d k%d s%d d%d @%dx%d", tcp ? (split ? "conv_c8_kernel (split-half fp16 x3)" : cw.use_c8 ? "conv_c8_kernel" : "conv_tc_kernel") : "conv_direct_kernel",
                s.deconv ? (grp ? (grp->ncls == 4 ? "deconv (4 classes fused)" : "deconv (2 classes fused)") : "deconv-class") : (L.fused_pair ? "stem pair" : "conv"), s.cin, s.cout, s.k, s.stride, s.rate, Ho * cw.osy, Wo * cw.osx);
       c.tag(buf, tcp ? 1 : 0, f_alg, f_exec, bytes);
     }
@@ -660,7 +702,7 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     else CK(launch_conv(c, cp, cw));
   }
   static const bool dbg = getenv("SE_DEBUG_NAN") != nullptr;
-  if (dbg && !c.dry && c.act_dt() == DT_BF16) {
+  if (dbg && !c.dry && c.act_dt() == DT_BF16 && !split) {
     const int cg = s.cout / 2, Hout = Ho * L.cls[0].osy, Wout = Wo * L.cls[0].osx;
     const long long n_out = out_c8 ? (long long)c.B * ldo * Hout * Wout * 8 : (long long)c.B * Hout * Wout * ldo;
     const long long n_in = in.c8 ? (long long)c.B * in.ld * in.H * (L.is_stem ? stem_wp(in.W) : in.W) * 8 / (in.c8 == 2 ? 4 : 1) : (long long)c.B * in.H * in.W * in.ld;
@@ -684,7 +726,7 @@ static int run_chain(Ctx& c, char net, const std::vector<std::string>& names, Vi
   View cur = in;
   Buf cur_buf = in_buf;
   bool cur_owned = free_in;
-  if (final_c8 < 0) final_c8 = (c.prec == SE_PREC_BF16_TC) ? 1 : 0;
+  if (final_c8 < 0) final_c8 = c.tc() ? 1 : 0;
   for (size_t i = 0; i < names.size(); ++i) {
     Layer* L = find_ready(c.m, net, names[i]);
     SE_REQUIRE(L != nullptr, "unknown or unloaded layer " + names[i] + ": " + last_error());
@@ -706,8 +748,8 @@ static int run_chain(Ctx& c, char net, const std::vector<std::string>& names, Vi
         oc8 = wants_c8(c, *nx);
       }
       nb = c.get(act_bytes(c, Ho, Wo, cg, oc8));
-      nxt = oc8 ? c8view(nb.p, Ho, Wo, cg, (cg + 7) / 8, 0) : nhwc(nb.p, Ho, Wo, cg, cg);
-      if (oc8 == 2) { nxt.c8 = 2; nxt.ld = 4 * (cg / 8); }   // [N][4*cg/8][Ho/2][Wo/2][8]
+      nxt = oc8 ? c8view(nb.p, Ho, Wo, cg, (cg + 7) / 8 * c.sp(), 0) : nhwc(nb.p, Ho, Wo, cg, cg);
+      if (oc8 == 2) { nxt.c8 = 2; nxt.ld = 4 * (cg / 8) * c.sp(); }   // [N][4*cg/8][Ho/2][Wo/2][8] (split-half: twice the blocks per parity)
       int rc = run_layer(c, *L, cur, nb.p, oc8 ? nxt.ld : cg, 0, oc8);
       if (rc) return rc;
     }
@@ -743,6 +785,12 @@ static int run_head(Ctx& c, char net, const std::string& name, const View& in, i
     c.tag(std::string(in.c8 == 1 && c.act_dt() == DT_BF16 ? "head_c8_kernel" : "head_kernel") + "|12->" + std::to_string(L->spec.cout) + " k3 + " +
               (mode == HEAD_MASK ? "sigmoid+threshold" : mode == HEAD_TANH ? "tanh" : mode == HEAD_COARSE ? "tanh+blend+pack8" : "tanh+soft blend"),
           0, fl, fl, bytes);
+  }
+  if (c.split()) {
+    SE_REQUIRE(in.c8 == 1 && in.ld == 4, "split-half head input: two channel blocks, hi + lo");
+    CK(head_split(in.p, L->w_head, L->bias, L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2, out_pack8,
+                  c.m->opt[SE_OPT_NO_MASK_COARSE], stem_wp(in.W), STEM_PADL, out_bs, msoft_bs, out_u8, c.stream));
+    return 0;
   }
   if (in.c8 == 1 && c.act_dt() == DT_BF16) {
     CK(head_c8(in.p, L->w_head_host.data(), L->b_host.data(), L->spec.cout, c.B, in.H, in.W, mode, img, mask_bin, mask_soft, out_nchw, out2,
@@ -887,6 +935,23 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
 static const std::initializer_list<const char*> kTrunk9 = {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5",
                                                            "conv6", "conv7_atrous", "conv8_atrous", "conv9_atrous"};
 
+// input packing / pooling glue in the activation storage of the current mode
+static int do_pack8(Ctx& c, const float* img, const float* sk, const float* mask, void* out, int H, int W, int img_mode, float sscale, int write_mask,
+                    int img2_mode = -1) {
+  if (c.split()) return pack8_split(img, sk, mask, out, c.B, H, W, stem_wp(W), STEM_PADL, img_mode, sscale, write_mask, c.stream);
+  return pack8(img, sk, mask, out, c.act_dt(), c.B, H, W, stem_wp(W), STEM_PADL, img_mode, sscale, write_mask, c.stream, img2_mode);
+}
+static int do_pool_broadcast(Ctx& c, const View& v, int HW, int mode, float* pooled, void* cat, int cat_ld, int tc) {
+  if (c.split()) {
+    int rc = plane_reduce_split(v.p, c.B, HW, 96, v.ld / 2, mode, pooled, c.stream);
+    if (rc) return rc;
+    return broadcast_split(pooled, cat, c.B, HW, 96, cat_ld / 2, 96, c.stream);
+  }
+  int rc = plane_reduce(v.p, c.act_dt(), c.B, HW, 96, v.ld, v.c8, mode, pooled, c.stream);
+  if (rc) return rc;
+  return broadcast_channels(pooled, cat, c.act_dt(), c.B, HW, 96, cat_ld, 96, tc, c.stream);
+}
+
 // MDGenerator.forward: x [B,3,H,W], guide [B,1,H,W] -> mask1 (soft, NCHW), optional x_stage1; also the
 // binarised mask plane (mask1 > 0.5) when mask_bin != nullptr.
 static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, float* mask1, float* x_stage1, float* mask_bin, long long mask1_bs = 0,
@@ -894,7 +959,7 @@ static int run_netM(Ctx& c, const float* x, const float* guide, int H, int W, fl
   const int dt = c.act_dt();
   Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * c.esz());
   c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
-  CK(pack8(x, guide, nullptr, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE, 1.0f, 0, c.stream));
+  CK(do_pack8(c, x, guide, nullptr, in8.p, H, W, PACK_IMG_ONE, 1.0f, 0));
   View x9;
   Buf b9;
   int rc = run_chain(c, 'M', with_prefix("", kTrunk9), stem_view(c, in8.p, H, W), true, in8, &x9, &b9);
@@ -937,22 +1002,21 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
   const size_t e = c.esz();
 
   // ---- stage 1: coarse encoder + style ("warp-in") encoder -> 192-channel concat -> coarse decoder
-  const int tc = (c.prec == SE_PREC_BF16_TC) ? 1 : 0;
-  const int cat_ld = tc ? 24 : 192;                    // 192-channel concat buffers: 24 channel blocks or pixel pitch 192
-  auto cat_view = [&](void* p) { return tc ? c8view(p, h, w, 192, 24, 0) : nhwc(p, h, w, 192, 192); };
+  const int tc = c.tc() ? 1 : 0;
+  const int cat_ld = tc ? 24 * c.sp() : 192;           // 192-channel concat buffers: 24 channel blocks (x2 split-half) or pixel pitch 192
+  auto cat_view = [&](void* p) { return tc ? c8view(p, h, w, 192, cat_ld, 0) : nhwc(p, h, w, 192, 192); };
   Buf cat1 = c.get((size_t)c.B * h * w * 192 * e);
   // stem pairs (tensor-core path, make_stem_pair): conv1 + wconv1 share one packed input when both encoders see the same image
   // and mask (always true on the inference path: netG(inputs, inputs, mask_bin, mask_bin, line))
-  Layer* pair1 = (tc && x == x2 && mask == mask2) ? find_layer(c.m, 'G', "conv1+wconv1") : nullptr;
-  Layer* pair2 = tc ? find_layer(c.m, 'G', "xconv1+pmconv1") : nullptr;
+  Layer* pair1 = (c.prec == SE_PREC_BF16_TC && x == x2 && mask == mask2) ? find_layer(c.m, 'G', "conv1+wconv1") : nullptr;
+  Layer* pair2 = c.prec == SE_PREC_BF16_TC ? find_layer(c.m, 'G', "xconv1+pmconv1") : nullptr;
   const size_t pair_bytes = (size_t)c.B * 24 * (H / 2) * (W / 2) * 16;   // two space-to-depth tensors of 24 channels
   auto pair_view = [&](void* p, int which) { View v = c8view(p, H, W, 24, 24, 12 * which); v.c8 = 2; return v; };
   std::vector<std::string> trunk_rest(kTrunk9.begin() + 1, kTrunk9.end());   // conv2_downsample .. conv9_atrous
   if (pair1) {
     Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
     c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
-    CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream,
-             opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M));
+    CK(do_pack8(c, x, guide, mask, in8.p, H, W, PACK_IMG_ONE_MINUS_M, 1.0f, 1, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M));
     Buf st = c.get(pair_bytes);
     int rc = run_layer(c, *pair1, stem_view(c, in8.p, H, W), st.p, 24, 0, 2);
     if (rc) return rc;
@@ -968,17 +1032,15 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     if (rc) return rc;
     c.put(st);
     Buf pooled = c.get((size_t)c.B * 96 * 4);
-    c.tag("plane_reduce|global style pooling", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
-    CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, v.c8, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
-    c.tag("broadcast_channels|pooled style vector -> concat blocks", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
-    CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, cat_ld, 96, tc, c.stream));
+    c.tag("plane_reduce + broadcast_channels|global style pooling -> concat blocks", 0, 0, 0, 2.0 * c.B * h * w * 96 * (c.esz() > 2 ? 4 : 2));
+    CK(do_pool_broadcast(c, v, h * w, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, cat1.p, cat_ld, tc));
     c.put(pooled);
     c.put(b);
   } else {
   {
       Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
       c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
-      CK(pack8(x, guide, mask, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, PACK_IMG_ONE_MINUS_M, 1.0f, 1, c.stream));
+      CK(do_pack8(c, x, guide, mask, in8.p, H, W, PACK_IMG_ONE_MINUS_M, 1.0f, 1));
       std::vector<std::string> names = with_prefix("", kTrunk9);
       names.push_back("conv10_atrous");
       int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, nullptr, nullptr, cat1.p, cat_ld, 0);
@@ -987,8 +1049,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     {
       Buf in8 = c.get((size_t)c.B * H * stem_wp(W) * 8 * e);
       c.tag("pack8_kernel|mask-mul + concat + cast", 0, 0, 0, (double)c.B * H * W * 20 + (double)c.B * H * stem_wp(W) * 8 * c.esz());
-      CK(pack8(x2, guide, mask2, in8.p, dt, c.B, H, W, stem_wp(W), STEM_PADL, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M,
-               opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f, 1, c.stream));
+      CK(do_pack8(c, x2, guide, mask2, in8.p, H, W, opt[SE_OPT_NO_MASK_CC] ? PACK_IMG_ONE : PACK_IMG_M, opt[SE_OPT_JOINT_TRAIN_INP] ? 0.0f : 1.0f, 1));
       std::vector<std::string> names = with_prefix("w", kTrunk9);
       names.push_back("wconv10_atrous");
       View v;
@@ -996,10 +1057,8 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
       int rc = run_chain(c, 'G', names, stem_view(c, in8.p, H, W), true, in8, &v, &b);
       if (rc) return rc;
       Buf pooled = c.get((size_t)c.B * 96 * 4);
-      c.tag("plane_reduce|global style pooling", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
-      CK(plane_reduce(v.p, dt, c.B, h * w, 96, v.ld, v.c8, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, c.stream));
-      c.tag("broadcast_channels|pooled style vector -> concat blocks", 0, 0, 0, (double)c.B * h * w * 96 * c.esz());
-      CK(broadcast_channels((const float*)pooled.p, cat1.p, dt, c.B, h * w, 96, cat_ld, 96, tc, c.stream));
+      c.tag("plane_reduce + broadcast_channels|global style pooling -> concat blocks", 0, 0, 0, 2.0 * c.B * h * w * 96 * (c.esz() > 2 ? 4 : 2));
+      CK(do_pool_broadcast(c, v, h * w, opt[SE_OPT_POOL_AVG] ? RED_AVG : RED_MAX, (float*)pooled.p, cat1.p, cat_ld, tc));
       c.put(pooled);
       c.put(b);
     }
@@ -1040,7 +1099,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
     View pm;
     Buf pmb;
     // pmconv6 writes the layout the attention reads: space-to-depth channel-blocked on the tensor-core path, NHWC otherwise
-    const int pm_c8 = opt[SE_OPT_USE_CAM] ? (tc ? 2 : 0) : -1;
+    const int pm_c8 = opt[SE_OPT_USE_CAM] ? (c.split() ? 1 : (tc ? 2 : 0)) : -1;
     int rc = pair2 ? run_chain(c, 'G', with_prefix("pm", {"conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}), pair_view(st2.p, 1), true, st2,
                                &pm, &pmb, nullptr, 0, 0, pm_c8)
                    : run_chain(c, 'G', with_prefix("pm", {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6"}),
@@ -1051,11 +1110,24 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
       c.tag("avgpool4_kernel", 0, 0, 0, (double)c.B * H * W * 4);
       CK(avgpool4(mask, (float*)ms.p, c.B, H, W, c.stream));
       Buf camo = c.get((size_t)c.B * h * w * 96 * e);
-      rc = tc ? run_cam_tc(c, pm, (const float*)ms.p, camo.p, nullptr) : run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr, 0);
-      if (rc) return rc;
+      if (c.split()) {
+        // split-half mode: the attention itself runs on the fp32 CUDA-core kernels (exact class) between two layout conversions
+        Buf f32 = c.get((size_t)c.B * h * w * 96 * 4), o32 = c.get((size_t)c.B * h * w * 96 * 4);
+        CK(split_to_f32(pm.p, (float*)f32.p, c.B, 96, h * w, pm.ld / 2, 0, 1, c.stream));
+        const int saved = c.prec;
+        c.prec = SE_PREC_FP32_EXACT;
+        rc = run_cam(c, nhwc(f32.p, h, w, 96, 96), (const float*)ms.p, o32.p, 96, nullptr, 0);
+        c.prec = saved;
+        if (rc) return rc;
+        CK(nhwc_f32_to_split((const float*)o32.p, camo.p, c.B, 96, h * w, 12, 0, c.stream));
+        c.put(o32); c.put(f32);
+      } else {
+        rc = tc ? run_cam_tc(c, pm, (const float*)ms.p, camo.p, nullptr) : run_cam(c, pm, (const float*)ms.p, camo.p, 96, nullptr, 0);
+        if (rc) return rc;
+      }
       c.put(ms);
       c.put(pmb);
-      pm = tc ? c8view(camo.p, h, w, 96, 12, 0) : nhwc(camo.p, h, w, 96, 96);
+      pm = tc ? c8view(camo.p, h, w, 96, 12 * c.sp(), 0) : nhwc(camo.p, h, w, 96, 96);
       pmb = camo;
     }
     rc = run_chain(c, 'G', with_prefix("pm", {"conv9", "conv10"}), pm, true, pmb, nullptr, nullptr, cat2.p, cat_ld, 96);
@@ -1085,7 +1157,7 @@ constexpr size_t kMaxGraphs = 16;
 template <typename F>
 static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, std::vector<uintptr_t> key = {}) {
   SE_REQUIRE(m && m->finalized, "model not finalized");
-  SE_REQUIRE(prec >= 0 && prec <= 2, "precision");
+  SE_REQUIRE(prec >= 0 && prec <= 3, "precision");
   std::lock_guard<std::mutex> model_lock(m->mu);
   {
     int dev = -1;
@@ -1393,13 +1465,19 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
   Layer* L = find_ready(m, net, layer);
   SE_REQUIRE(L != nullptr, std::string("no such (loaded) layer: ") + layer);
   cudaStream_t st = (cudaStream_t)stream;
+  // heads are raw fp32 CUDA-core convolutions in every mode; the fp32-on-tensor-cores mode runs them like the fp32 path
+  if (precision == SE_PREC_FP32_TC && L->is_head) precision = SE_PREC_FP32_EXACT;
   return with_arena(m, precision, B, st, [&](Ctx& c) -> int {
     const Spec& s = L->spec;
     const int dt = c.act_dt();
     const int Ci = L->is_head ? 12 : L->Ci;
     const int in_c8 = wants_c8(c, *L);
     Buf in = c.get(L->is_stem ? (size_t)B * H * stem_wp(W) * 8 * c.esz() : act_bytes(c, H, W, Ci, in_c8));
-    if (L->is_stem) {
+    if (c.split()) {
+      // split-half storage: hi / lo fp16 halves of the fp32 input in the layout the layer reads
+      if (L->is_stem || s.cin % 8) CK(fill_zero(in.p, in.bytes, st));
+      CK(nchw_to_split(x, in.p, B, s.cin, H, W, L->is_stem ? 3 : in_c8, stem_wp(W), STEM_PADL, st));
+    } else if (L->is_stem) {
       CK(fill_zero(in.p, in.bytes, st));
       CK(nchw_to_stem8(x, in.p, dt, B, s.cin, H, W, stem_wp(W), STEM_PADL, st));
     } else if (in_c8 == 2) {
@@ -1430,13 +1508,23 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
       c.put(o);
     } else {
       const int cg = s.cout / 2;
-      Buf o = c.get((size_t)B * Ho * Wo * cg * c.esz());
-      View vin = L->is_stem ? stem_view(c, in.p, H, W) : (in_c8 ? c8view(in.p, H, W, Ci, (Ci + 7) / 8, 0) : nhwc(in.p, H, W, Ci, Ci));
-      if (in_c8 == 2) { vin.c8 = 2; vin.ld = 4 * (Ci / 8); }
-      int r = run_layer(c, *L, vin, o.p, cg, 0, 0);
-      if (r) return r;
-      CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, st));
-      c.put(o);
+      View vin = L->is_stem ? stem_view(c, in.p, H, W) : (in_c8 ? c8view(in.p, H, W, Ci, (Ci + 7) / 8 * c.sp(), 0) : nhwc(in.p, H, W, Ci, Ci));
+      if (in_c8 == 2) { vin.c8 = 2; vin.ld = 4 * (Ci / 8) * c.sp(); }
+      if (c.split()) {
+        const int cbo = (cg + 7) / 8;
+        Buf o = c.get(act_bytes(c, Ho, Wo, cg, 1));
+        if (cg % 8) CK(fill_zero(o.p, o.bytes, st));
+        int r = run_layer(c, *L, vin, o.p, 2 * cbo, 0, 1);
+        if (r) return r;
+        CK(split_to_f32(o.p, y, B, cg, Ho * Wo, cbo, 0, 0, st));
+        c.put(o);
+      } else {
+        Buf o = c.get((size_t)B * Ho * Wo * cg * c.esz());
+        int r = run_layer(c, *L, vin, o.p, cg, 0, 0);
+        if (r) return r;
+        CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, st));
+        c.put(o);
+      }
     }
     c.put(in);
     return 0;
@@ -1450,6 +1538,7 @@ int se_contextual_attention_forward(const float* feat, const float* mask_s, int 
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   if (!holder) { holder = new se_model(); holder->finalized = true; }
+  if (precision == SE_PREC_FP32_TC) precision = SE_PREC_FP32_EXACT;   // the attention of the fp32 modes runs on the fp32 CUDA-core kernels
   cudaStream_t st = (cudaStream_t)stream;
   return with_arena(holder, precision, B, st, [&](Ctx& c) -> int {
     const int dt = c.act_dt();

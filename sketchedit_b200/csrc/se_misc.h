@@ -34,6 +34,17 @@ int nchw_to_nhwc(const float* x, void* y, int dt, int B, int C, int HW, int ldo,
 int nhwc_to_nchw(const void* x, int dt, float* y, int B, int C, int HW, int ldx, int choff, cudaStream_t s);
 int u8_to_inputs(const unsigned char* img_u8, const unsigned char* sk_u8, float* img, float* sk, int B, int H, int W, cudaStream_t s);
 int to_uint8(const float* comp, const float* mask, unsigned char* bgr, unsigned char* mk, int B, int H, int W, cudaStream_t s);
+// split-half twins (se_split.cu): activations stored as fp16 hi + fp16 lo (DT_F16X2)
+int pack8_split(const float* img, const float* sketch, const float* mask, void* out, int B, int H, int W, int Wp, int padl, int img_mode,
+                float sketch_scale, int write_mask, cudaStream_t s);
+int head_split(const void* x, const float* w, const float* bias, int cout, int B, int H, int W, int mode, const float* img, const float* mask_bin,
+               const float* mask_soft, float* out_nchw, float* out2, void* out_pack8, int no_mask_coarse, int Wp, int padl, long long obs, long long msbs,
+               unsigned char* out_u8, cudaStream_t s);
+int plane_reduce_split(const void* x, int B, int HW, int C, int ld, int mode, float* out, cudaStream_t s);
+int broadcast_split(const float* v, void* y, int B, int HW, int C, int ld, int choff, cudaStream_t s);
+int nchw_to_split(const float* x, void* y, int B, int C, int H, int W, int layout, int Wp, int padl, cudaStream_t s);
+int split_to_f32(const void* x, float* y, int B, int C, int HW, int ld, int choff, int nhwc, cudaStream_t s);
+int nhwc_f32_to_split(const float* x, void* y, int B, int C, int HW, int ld, int choff, cudaStream_t s);
 long long count_nonfinite_bf16(const void* x, long long n, cudaStream_t s);
 int fill_zero(void* p, size_t bytes, cudaStream_t s);
 

@@ -1,6 +1,8 @@
 // Device-side building blocks shared by the tcgen05 convolution kernels (se_conv_tc.cu: NHWC input,
 // se_conv_c8.cu: channel-blocked input): mbarrier / TMA / tcgen05 PTX wrappers and the fused epilogue.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "se_common.cuh"
 
 namespace se {
@@ -444,6 +446,65 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
     }
   } else {
     for (int b = grp; b < nb; b += nsplit) do8(b);
+  }
+}
+
+// Split-half mode (DT_F16X2, the fp32-on-tensor-cores path): same gate, fp32-accurate math (ex2 / rcp approximations are good
+// to ~2^-22; no tanh.approx), each output stored as hi = fp16(v) and lo = fp16(v - hi), the lo block split_stride further on.
+// The accumulator column of a gate still holds 0.5 * g (weights are packed pre-multiplied by 0.5, exact), hb = 0.5 * b'.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool kElu>
+__device__ __forceinline__ float gate_one_exact(float f, float ghalf, float b, float hb) {
+  const float fv = f + b;
+  float a;
+  if (kElu) a = fv > 0.0f ? fv : (ex2_approx(fv * 1.4426950408889634f) - 1.0f);
+  else a = fmaxf(fv, 0.0f);
+  const float gx = 2.0f * (ghalf + hb);
+  return a * rcp_approx(1.0f + ex2_approx(-gx * 1.4426950408889634f));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <bool kElu>
+__device__ __forceinline__ void tc_epilogue_gated_split(const EpiParams& e, const float* cst, int cst_n, uint32_t taddr, int img, bool valid,
+                                                        int oy, int ox, int grp, int nsplit) {
+  const int half = e.Cout >> 1, goff = e.goff;
+  const int nb = (half + 7) >> 3;
+  uint4* const ybase = reinterpret_cast<uint4*>(e.y);
+  uint32_t obase, ostep;
+  if (e.out_c8 == 2) {
+    const uint32_t Hs = e.Hout >> 1, Ws = e.Wout >> 1, par = ((oy & 1) << 1) | (ox & 1);
+    ostep = Hs * Ws;
+    obase = (((uint32_t)img * e.ldo + par * (uint32_t)e.par_stride + (e.choff >> 3)) * Hs + (oy >> 1)) * Ws + (ox >> 1);
+  } else {
+    ostep = (uint32_t)e.Hout * e.Wout;
+    obase = (((uint32_t)img * e.ldo + (e.choff >> 3)) * e.Hout + oy) * e.Wout + ox;
+  }
+  for (int b = grp; b < nb; b += nsplit) {
+    const int c0 = b * 8;
+    float f[8], g[8];
+    tmem_ld8(taddr + c0, f);
+    tmem_ld8(taddr + goff + c0, g);
+    tmem_ld_wait();
+    if (valid) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const float v0 = gate_one_exact<kElu>(f[k], g[k], cst[c0 + k], cst[2 * cst_n + goff + c0 + k]);
+        const float v1 = gate_one_exact<kElu>(f[k + 1], g[k + 1], cst[c0 + k + 1], cst[2 * cst_n + goff + c0 + k + 1]);
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        hi[k >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lo[k >> 1] = pack_f16x2(v0 - __half2float(h0), v1 - __half2float(h1));
+      }
+      const uint32_t o = obase + (uint32_t)b * ostep + (b >= e.blk_split ? (uint32_t)e.blk_jump : 0u);
+      ybase[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      ybase[o + (uint32_t)e.split_stride] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 

@@ -18,7 +18,7 @@ from sketchedit_b200 import synth
 from tests.util_parity import engine, maxdiff, weights
 
 pytestmark = pytest.mark.gpu
-TOL = {"fp32": 1e-3, "bf16": 1e-2}
+TOL = {"fp32": 1e-3, "fp32_direct": 1e-3, "bf16": 1e-2}   # "fp32": split-half tensor-core arithmetic, "fp32_direct": CUDA cores
 
 
 def _golden_inputs(z):
@@ -29,7 +29,7 @@ def _golden_inputs(z):
     return image, sketch
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32_direct", "bf16"])
 def test_netM(prec):
     WM, _ = weights()
     img, sk = synth.synth_inputs(2, 64, 96, seed=11)
@@ -39,7 +39,7 @@ def test_netM(prec):
     assert maxdiff(st1.cpu(), rs) <= TOL[prec]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32_direct", "bf16"])
 def test_netG(prec):
     _, WG = weights()
     img, sk = synth.synth_inputs(2, 64, 64, seed=12)
@@ -52,7 +52,7 @@ def test_netG(prec):
     assert maxdiff(s2.cpu(), r2) <= TOL[prec], maxdiff(s2.cpu(), r2)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32_direct", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 64, 64), (1, 96, 64), (1, 128, 104)])
 def test_inference_vs_oracle(prec, shape):
     WM, WG = weights()
@@ -62,7 +62,7 @@ def test_inference_vs_oracle(prec, shape):
     ours_bin = ex["mask_bin"].cpu()
     ref_free = O.inference(WM, WG, img, sk)
     flips = int((ours_bin != ref_free["mask_bin"]).sum())
-    assert flips <= (0 if prec == "fp32" else 0.02 * ours_bin.numel()), flips
+    assert flips <= (0 if prec.startswith("fp32") else 0.02 * ours_bin.numel()), flips
     ref = O.inference(WM, WG, img, sk, mask_bin_override=ours_bin)
     assert maxdiff(mask.cpu(), ref["mask"]) <= TOL[prec]
     for k, t in (("coarse", ex["coarse"]), ("fine", ex["fine"]), ("composed", composed)):
@@ -71,13 +71,15 @@ def test_inference_vs_oracle(prec, shape):
 
 @pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in
                                         glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))))
-def test_fp32_path_matches_reference_golden(name, golden_dir):
-    """fp32 path vs outputs of the unmodified reference (tests/golden, oracle/make_golden.py)."""
+@pytest.mark.parametrize("prec", ["fp32", "fp32_direct"])
+def test_fp32_path_matches_reference_golden(name, golden_dir, prec):
+    """fp32 paths (tensor-core split-half arithmetic and the CUDA-core cross-check) vs outputs of the unmodified reference
+    (tests/golden, oracle/make_golden.py)."""
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     image, sketch = _golden_inputs(z)
     flags = dict(eval(str(z["flags"])))
     eng = engine(**flags)
-    composed, mask, ex = eng.inference(image.cuda(), sketch.cuda(), precision="fp32", want=("fine", "mask_bin"))
+    composed, mask, ex = eng.inference(image.cuda(), sketch.cuda(), precision=prec, want=("fine", "mask_bin"))
     ref_bin = (torch.from_numpy(z["mask"]) > 0.5).float()
     assert int((ex["mask_bin"].cpu() != ref_bin).sum()) == 0
     assert maxdiff(mask.cpu(), torch.from_numpy(z["mask"])) <= 1e-3

@@ -1,6 +1,8 @@
 """GPU parity of the operators behind gen_conv / gen_deconv / contextual attention, through the C ABI.
 
-fp32 mode  : CUDA-core fp32 kernels vs the fp32 oracle, tolerance 1e-4 (abs, activations are O(1)).
+fp32 mode  : "fp32" = fp32-parity arithmetic on the tensor cores (split-half fp16 operands, three tcgen05 products per tap),
+             "fp32_direct" = the fp32 CUDA-core kernels (its cross-check); both vs the fp32 oracle, tolerance 1e-4 (abs,
+             activations are O(1)).
 bf16 mode  : tcgen05 kernels vs the oracle evaluated on the SAME bf16-rounded inputs and weights, so the
              only differences are fp32 accumulation order and the final bf16 rounding of the output:
              tolerance 2^-8 relative to max|y| (one bf16 ulp at the top of the range) + 1e-3.
@@ -42,11 +44,13 @@ LAYER_CASES = [
 ]
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp32_direct"])
 @pytest.mark.parametrize("net,name,H,W", LAYER_CASES)
-def test_gated_conv_fp32(net, name, H, W):
+def test_gated_conv_fp32(net, name, H, W, prec):
     spec = layer_map(net)[name]
     x = rand_act((2, spec.cin, H, W), seed=hash((net, name)) % 1000)
-    y = engine().gated_conv(net, name, x.cuda(), precision="fp32").cpu()
+    x = x + 1e-3 * rand_act((2, spec.cin, H, W), seed=hash((net, name)) % 1000 + 1)      # not bf16-representable: the lo halves matter
+    y = engine().gated_conv(net, name, x.cuda(), precision=prec).cpu()
     ref = oracle_layer(net, name, x, bf16_weights=False)
     assert y.shape == ref.shape
     assert maxdiff(y, ref) <= 1e-4, (name, maxdiff(y, ref))
