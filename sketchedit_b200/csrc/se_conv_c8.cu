@@ -488,7 +488,7 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
   // so the MMAs never multiply stale shared memory (possibly NaN bit patterns) by the zero weight columns
   // (space-to-depth layers: a tap starts at its own channel block; the zero weight columns of its last chunk may then
   //  multiply the next parity's finite activations instead of TMA zeros, which is just as harmless)
-  L->cb_in = stem ? 1 : cb_max + (w.n64 * 64 + w.n32 * 32) / 8;
+  L->cb_in = stem ? 1 + cb_max : cb_max + (w.n64 * 64 + w.n32 * 32) / 8;   // (split-half stem input: hi block + lo block)
   const long long halo_bytes = (long long)L->cb_in * HR * WR * 16;
   w.NT = (gated_goff(Cout) + Cout / 2 + 15) / 16 * 16;   // every layer on this path is gated: gate columns start at goff
   w.n_tiles = 1;
