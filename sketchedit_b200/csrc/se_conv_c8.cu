@@ -99,10 +99,14 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // has four tile-times per tile); wider tiles keep 2 stages and split a tile's columns between the groups.
   // N <= 64 even fits 8 stages, two per group: while a group drains tile i the MMAs of tile i+4 already fill its second
   // stage, so a group's cycle is the drain alone instead of drain + MMA latency (the small-N layers are epilogue bound)
-  const int acc_shift = p.NT <= 64 ? 3 : (p.NT <= 128 ? 2 : 1);
-  const int acc_stages = 1 << acc_shift;
-  const int acc_stride = 512 >> acc_shift;
-  const int epi_split = acc_stages >= 4 ? 1 : TC_EPI_GROUPS;
+  // (the launcher picks the ring sizes: powers of two, or 6 / 3 when three MMA issuer warps share the work - see c8_launch)
+  const int acc_stages = p.acc_stages, acc_stride = p.acc_stride;
+  const int epi_split = p.epi_split;
+  // slot / phase parity of iteration i in a ring of n slots (shift = log2 n, or < 0: n is not a power of two)
+  auto ring_of = [](int i, int n, int shift, int& slot, uint32_t& phase) {
+    if (shift >= 0) { slot = i & (n - 1); phase = (uint32_t)(i >> shift) & 1u; }
+    else { const int qd = i / n; slot = i - qd * n; phase = (uint32_t)qd & 1u; }
+  };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(wres_bar + 1);
   float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 16 B aligned: read with ld.shared.v4
 
@@ -174,8 +178,9 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int x0 = tx * C8_TW, y0 = ty * C8_TH;
       if (halo) {
-        const int ab = iter & (p.a_bufs - 1);                          // power-of-two ring, no integer division: stays uniform
-        const uint32_t aphase = (iter >> p.a_shift) & 1;
+        int ab;
+        uint32_t aphase;
+        ring_of(iter, p.a_bufs, p.a_shift, ab, aphase);
         const long long tw = p.dbg ? clock64() : 0;
         mbar_wait(&a_empty[ab], aphase ^ 1, 5);
         if (p.dbg) t_wait += clock64() - tw;
@@ -217,7 +222,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
-  } else if ((warp == 1 || (warp == 3 && !staged)) && (!kPair || cta_rank == 0)) {
+  } else if ((warp == 1 || ((warp == 3 || warp == 2) && !staged)) && (!kPair || cta_rank == 0)) {
     // ==================================================================== MMA issuer (pair: the leader, for both CTAs)
     // Nothing streamed per k-step (resident weights + halo): a tile is ONE short burst of MMAs, and the issuer's
     // per-tile protocol (two commits, two barrier waits, fence, descriptor set-up: ~600 cycles measured) is longer
@@ -226,160 +231,178 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The issuer count must divide every ring it indexes (TMEM stages, halo buffers): a ring slot is then always
     // handled by the same warp, in order - with slots shared between issuers a warp could test a barrier two phases
     // ahead, and mbarrier parity waits alias modulo 2 (a 3-issuer experiment corrupted tiles and hung exactly so).
-    const int n_issuers = (!staged && (p.a_bufs & 1) == 0 && (acc_stages & 1) == 0) ? 2 : 1;
-    const int me = (warp == 3) ? 1 : 0;   // a second issuer that is not needed simply finds no tile below
-    // D = f32; A, B = bf16 (format 1) or fp16 (format 0, split-half mode), both K-major; N = NT; M = 128 / 256
-    const uint32_t idesc = (1u << 4) | (p.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
-    int stage = 0;
-    uint32_t phase = 0;
-    long long t_wfull = 0, t_wtmem = 0, t_whalo = 0, t_begin = clock64();
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t off_wres = halo ? (uint32_t)(p.a_bufs * p.a_bytes) : 0u;
-    const uint32_t off_stages = off_wres + (p.resident ? (uint32_t)p.wres_bytes : 0u);
-    if (p.resident) mbar_wait(wres_bar, 0, 6);
-    if constexpr (NCLS > 1) {
-      // ------------------------------------------------ fused deconv classes (the launcher guarantees two issuers)
-      constexpr int CSH = NCLS == 4 ? 2 : 1;
-      const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-      const int nv = my_tiles * NCLS;
-      const uint32_t a_lo = ((p.lbo_bytes >> 4) & 0x3FFF) << 16;
-      const uint32_t a_hi = ((p.sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
-      const uint32_t b_hi128 = (1024u >> 4) | (1u << 14) | (2u << 29), b_hi64 = (512u >> 4) | (1u << 14) | (4u << 29);
-      const uint32_t kstep16 = p.kstep_bytes >> 4;
-      for (int v = me; v < nv; v += 2) {
-        const int riter = v >> CSH, cls = v & (NCLS - 1);
-        const int as = v & (acc_stages - 1);
-        const uint32_t accphase = (v >> acc_shift) & 1;
+    auto run_issuer = [&](auto ME_) {
+      const int n_issuers = staged ? 1 : p.niss;   // warps 1, 3, 2 (in this order); the launcher makes both rings multiples of it
+      // `me` (which of the two issuers this warp is; a second issuer that is not needed simply finds no tile below) is a
+      // COMPILE-TIME constant of each copy of this code: everything the MMA operands depend on (tile index, halo buffer, TMEM
+      // stage) then derives from blockIdx / parameters / loop counters only, so ptxas keeps the descriptor arithmetic on the
+      // uniform datapath. With `me` computed from the (shuffled) warp index it saw a divergent value and fed every UTCHMMA
+      // through 6-8 R2UR.BROADCAST moves: ~80 cycles of issue per MMA against 44 cycles of pipe time (ncu: tensor pipe 35 %
+      // active on the stems).
+      constexpr int me = decltype(ME_)::value;
+      // D = f32; A, B = bf16 (format 1) or fp16 (format 0, split-half mode), both K-major; N = NT; M = 128 / 256
+      const uint32_t idesc = (1u << 4) | (p.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long t_wfull = 0, t_wtmem = 0, t_whalo = 0, t_begin = clock64();
+      const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+      const uint32_t off_wres = halo ? (uint32_t)(p.a_bufs * p.a_bytes) : 0u;
+      const uint32_t off_stages = off_wres + (p.resident ? (uint32_t)p.wres_bytes : 0u);
+      if (p.resident) mbar_wait(wres_bar, 0, 6);
+      if constexpr (NCLS > 1) {
+        // ------------------------------------------------ fused deconv classes (the launcher guarantees two issuers)
+        constexpr int CSH = NCLS == 4 ? 2 : 1;
+        const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int nv = me < 2 ? my_tiles * NCLS : 0;   // two issuers (the classes alternate by parity)
+        const uint32_t a_lo = ((p.lbo_bytes >> 4) & 0x3FFF) << 16;
+        const uint32_t a_hi = ((p.sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
+        const uint32_t b_hi128 = (1024u >> 4) | (1u << 14) | (2u << 29), b_hi64 = (512u >> 4) | (1u << 14) | (4u << 29);
+        const uint32_t kstep16 = p.kstep_bytes >> 4;
+        for (int v = me; v < nv; v += 2) {
+          const int riter = v >> CSH, cls = v & (NCLS - 1);
+          int as;
+          uint32_t accphase;
+          ring_of(v, acc_stages, p.acc_shift, as, accphase);
+          long long tw = p.dbg ? clock64() : 0;
+          mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
+          if (p.dbg) t_wtmem += clock64() - tw;
+          int ab;
+          uint32_t aph;
+          ring_of(riter, p.a_bufs, p.a_shift, ab, aph);
+          tw = p.dbg ? clock64() : 0;
+          mbar_wait(&a_full[ab], aph, 7);
+          if (p.dbg) t_whalo += clock64() - tw;
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + as * acc_stride;
+          const uint32_t sA = smem_base + (uint32_t)ab * p.a_bytes;
+          const uint32_t sB = smem_base + off_wres + (uint32_t)cls * (uint32_t)p.cls_bytes;
+          const uint32_t lead = elect_one() ? 1u : 0u;
+          auto issue_cls = [&](auto CLS) {
+            constexpr int C = decltype(CLS)::value;
+            uint32_t acc = 0u;
+  #pragma unroll
+            for (int j = 0; j < R64; ++j) {
+              const uint32_t a0 = (sA + p.aoff[C * C8_CLS_UNITS + j]) >> 4;
+              const uint32_t b0 = (sB + j * b64_bytes) >> 4;
+  #pragma unroll
+              for (int k = 0; k < MMAS; ++k) {
+                umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+                acc = 1u;
+              }
+            }
+  #pragma unroll
+            for (int j = 0; j < R32; ++j) {
+              const uint32_t a0 = (sA + p.aoff[C * C8_CLS_UNITS + R64 + j]) >> 4;
+              const uint32_t b0 = (sB + R64 * b64_bytes + j * b32_bytes) >> 4;
+  #pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
+                acc = 1u;
+              }
+            }
+          };
+          if (cls == 0) issue_cls(std::integral_constant<int, 0>{});
+          else if (cls == 1) issue_cls(std::integral_constant<int, 1>{});
+          else if (NCLS == 4 && cls == 2) issue_cls(std::integral_constant<int, NCLS == 4 ? 2 : 0>{});
+          else issue_cls(std::integral_constant<int, NCLS == 4 ? 3 : 1>{});
+          if (cls >= NCLS - 2) umma_commit_if(lead, &a_empty[ab]);   // this issuer's last class of the tile
+          umma_commit_if(lead, &tmem_full[as]);
+          __syncwarp();
+        }
+      } else {
+      for (int iter = me, tile = (me < n_issuers) ? (int)(blockIdx.x + me * gridDim.x) : total_tiles; tile < total_tiles;
+           tile += n_issuers * gridDim.x, iter += n_issuers) {
+        int as;
+        uint32_t accphase;
+        ring_of(iter, acc_stages, p.acc_shift, as, accphase);
         long long tw = p.dbg ? clock64() : 0;
-        mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
+        if (kPair) mbar_wait_cluster(&tmem_empty[as], accphase ^ 1, 2); else mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
         if (p.dbg) t_wtmem += clock64() - tw;
-        const int ab = riter & (p.a_bufs - 1);
-        tw = p.dbg ? clock64() : 0;
-        mbar_wait(&a_full[ab], (riter >> p.a_shift) & 1, 7);
-        if (p.dbg) t_whalo += clock64() - tw;
+        int ab = 0;
+        if (halo) {
+          uint32_t aph;
+          ring_of(iter, p.a_bufs, p.a_shift, ab, aph);
+          tw = p.dbg ? clock64() : 0;
+          mbar_wait(&a_full[ab], aph, 7);
+          if (p.dbg) t_whalo += clock64() - tw;
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * acc_stride;
-        const uint32_t sA = smem_base + (uint32_t)ab * p.a_bytes;
-        const uint32_t sB = smem_base + off_wres + (uint32_t)cls * (uint32_t)p.cls_bytes;
-        const uint32_t lead = elect_one() ? 1u : 0u;
-        auto issue_cls = [&](auto CLS) {
-          constexpr int C = decltype(CLS)::value;
-          uint32_t acc = 0u;
-#pragma unroll
-          for (int j = 0; j < R64; ++j) {
-            const uint32_t a0 = (sA + p.aoff[C * C8_CLS_UNITS + j]) >> 4;
-            const uint32_t b0 = (sB + j * b64_bytes) >> 4;
-#pragma unroll
-            for (int k = 0; k < MMAS; ++k) {
-              umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
-              acc = 1u;
-            }
+        for (int ks = 0; ks < (KS1 ? 1 : ksteps); ++ks) {
+          if (staged) {
+            tw = p.dbg ? clock64() : 0;
+            mbar_wait(&full_bar[stage], phase, 3);
+            if (p.dbg) t_wfull += clock64() - tw;
+            tc_fence_after();
           }
-#pragma unroll
-          for (int j = 0; j < R32; ++j) {
-            const uint32_t a0 = (sA + p.aoff[C * C8_CLS_UNITS + R64 + j]) >> 4;
-            const uint32_t b0 = (sB + R64 * b64_bytes + j * b32_bytes) >> 4;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
-              acc = 1u;
+          // shared-window addresses as plain 32-bit integer arithmetic on the (constant) window base: stays uniform
+          const uint32_t st = smem_base + off_stages + (uint32_t)stage * stage_bytes;
+          const uint32_t sB = p.resident ? smem_base + off_wres + (KS1 ? 0u : (uint32_t)ks * b_bytes) : st + stage_a;
+          const uint32_t sA = halo ? smem_base + (uint32_t)ab * p.a_bytes : st;
+          {
+            const uint32_t lead = elect_one() ? 1u : 0u;   // predicate only: no divergent region around the issue loop
+            uint32_t acc = (!KS1 && ks) ? 1u : 0u;
+            // descriptors: only the 14-bit start-address field (bytes >> 4) changes between MMAs
+            const uint32_t a_lo = ((p.lbo_bytes >> 4) & 0x3FFF) << 16;
+            const uint32_t a_hi = ((p.sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
+            const uint32_t b_hi128 = (1024u >> 4) | (1u << 14) | (2u << 29), b_hi64 = (512u >> 4) | (1u << 14) | (4u << 29);
+            const uint32_t kstep16 = p.kstep_bytes >> 4;
+            const uint32_t n_u64 = p.ntaps * p.n64;
+            // A offsets come from the constant bank (compile-time indices when the k-step structure is templated)
+            const int u0 = KS1 ? 0 : ks * r64, v0 = KS1 ? R64 : (int)n_u64 + ks * r32;
+  #pragma unroll
+            for (int j = 0; j < (R64 >= 0 ? R64 : 32); ++j) {
+              if (j < r64) {
+                const uint32_t a0 = (sA + p.aoff[u0 + j]) >> 4;
+                const uint32_t b0 = (sB + j * b64_bytes) >> 4;
+  #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < mmas64) {
+                    if (kPair) umma2_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+                    else umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+                    acc = 1u;
+                  }
+                }
+              }
             }
-          }
-        };
-        if (cls == 0) issue_cls(std::integral_constant<int, 0>{});
-        else if (cls == 1) issue_cls(std::integral_constant<int, 1>{});
-        else if (NCLS == 4 && cls == 2) issue_cls(std::integral_constant<int, NCLS == 4 ? 2 : 0>{});
-        else issue_cls(std::integral_constant<int, NCLS == 4 ? 3 : 1>{});
-        if (cls >= NCLS - 2) umma_commit_if(lead, &a_empty[ab]);   // this issuer's last class of the tile
-        umma_commit_if(lead, &tmem_full[as]);
-        __syncwarp();
-      }
-    } else {
-    for (int iter = me, tile = (me < n_issuers) ? (int)(blockIdx.x + me * gridDim.x) : total_tiles; tile < total_tiles;
-         tile += n_issuers * gridDim.x, iter += n_issuers) {
-      const int as = iter & (acc_stages - 1);
-      const uint32_t accphase = (iter >> acc_shift) & 1;
-      long long tw = p.dbg ? clock64() : 0;
-      if (kPair) mbar_wait_cluster(&tmem_empty[as], accphase ^ 1, 2); else mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
-      if (p.dbg) t_wtmem += clock64() - tw;
-      const int ab = halo ? (iter & (p.a_bufs - 1)) : 0;
-      if (halo) {
-        tw = p.dbg ? clock64() : 0;
-        mbar_wait(&a_full[ab], (iter >> p.a_shift) & 1, 7);
-        if (p.dbg) t_whalo += clock64() - tw;
-      }
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * acc_stride;
-      for (int ks = 0; ks < (KS1 ? 1 : ksteps); ++ks) {
-        if (staged) {
-          tw = p.dbg ? clock64() : 0;
-          mbar_wait(&full_bar[stage], phase, 3);
-          if (p.dbg) t_wfull += clock64() - tw;
-          tc_fence_after();
-        }
-        // shared-window addresses as plain 32-bit integer arithmetic on the (constant) window base: stays uniform
-        const uint32_t st = smem_base + off_stages + (uint32_t)stage * stage_bytes;
-        const uint32_t sB = p.resident ? smem_base + off_wres + (KS1 ? 0u : (uint32_t)ks * b_bytes) : st + stage_a;
-        const uint32_t sA = halo ? smem_base + (uint32_t)ab * p.a_bytes : st;
-        {
-          const uint32_t lead = elect_one() ? 1u : 0u;   // predicate only: no divergent region around the issue loop
-          uint32_t acc = (!KS1 && ks) ? 1u : 0u;
-          // descriptors: only the 14-bit start-address field (bytes >> 4) changes between MMAs
-          const uint32_t a_lo = ((p.lbo_bytes >> 4) & 0x3FFF) << 16;
-          const uint32_t a_hi = ((p.sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
-          const uint32_t b_hi128 = (1024u >> 4) | (1u << 14) | (2u << 29), b_hi64 = (512u >> 4) | (1u << 14) | (4u << 29);
-          const uint32_t kstep16 = p.kstep_bytes >> 4;
-          const uint32_t n_u64 = p.ntaps * p.n64;
-          // A offsets come from the constant bank (compile-time indices when the k-step structure is templated)
-          const int u0 = KS1 ? 0 : ks * r64, v0 = KS1 ? R64 : (int)n_u64 + ks * r32;
-#pragma unroll
-          for (int j = 0; j < (R64 >= 0 ? R64 : 32); ++j) {
-            if (j < r64) {
-              const uint32_t a0 = (sA + p.aoff[u0 + j]) >> 4;
-              const uint32_t b0 = (sB + j * b64_bytes) >> 4;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < mmas64) {
-                  if (kPair) umma2_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
-                  else umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi128, idesc, acc);
+  #pragma unroll
+            for (int j = 0; j < (R64 >= 0 ? R32 : 32); ++j) {
+              if (j < r32) {
+                const uint32_t a0 = (sA + p.aoff[v0 + j]) >> 4;
+                const uint32_t b0 = (sB + r64 * b64_bytes + j * b32_bytes) >> 4;
+  #pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  if (kPair) umma2_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
+                  else umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
                   acc = 1u;
                 }
               }
             }
-          }
-#pragma unroll
-          for (int j = 0; j < (R64 >= 0 ? R32 : 32); ++j) {
-            if (j < r32) {
-              const uint32_t a0 = (sA + p.aoff[v0 + j]) >> 4;
-              const uint32_t b0 = (sB + r64 * b64_bytes + j * b32_bytes) >> 4;
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                if (kPair) umma2_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
-                else umma_bf16_if32(lead, tmem_d, a_lo | (a0 + k * kstep16), a_hi, b0 + 2 * k, b_hi64, idesc, acc);
-                acc = 1u;
+            if (kPair) {
+              if (staged) umma2_commit_if(lead, &empty_bar[stage]);
+              if (KS1 || ks == ksteps - 1) {
+                if (halo) umma2_commit_if(lead, &a_empty[ab]);
+                umma2_commit_if(lead, &tmem_full[as]);
+              }
+            } else {
+              if (staged) umma_commit_if(lead, &empty_bar[stage]);
+              if (KS1 || ks == ksteps - 1) {
+                if (halo) umma_commit_if(lead, &a_empty[ab]);
+                umma_commit_if(lead, &tmem_full[as]);
               }
             }
           }
-          if (kPair) {
-            if (staged) umma2_commit_if(lead, &empty_bar[stage]);
-            if (KS1 || ks == ksteps - 1) {
-              if (halo) umma2_commit_if(lead, &a_empty[ab]);
-              umma2_commit_if(lead, &tmem_full[as]);
-            }
-          } else {
-            if (staged) umma_commit_if(lead, &empty_bar[stage]);
-            if (KS1 || ks == ksteps - 1) {
-              if (halo) umma_commit_if(lead, &a_empty[ab]);
-              umma_commit_if(lead, &tmem_full[as]);
-            }
-          }
+          __syncwarp();
+          if (staged && ++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (staged && ++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-    }
-    }   // NCLS == 1
-    if (p.dbg && lane == 0 && warp == 1) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 7] = t_whalo; }
+      }   // NCLS == 1
+
+      if (p.dbg && lane == 0 && me == 0) { p.dbg[blockIdx.x * 8 + 2] = t_wfull; p.dbg[blockIdx.x * 8 + 3] = t_wtmem; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 7] = t_whalo; }
+    };
+    if (warp == 1) run_issuer(std::integral_constant<int, 0>{});
+    else if (warp == 3) run_issuer(std::integral_constant<int, 1>{});
+    else run_issuer(std::integral_constant<int, 2>{});
   } else if (warp >= 4) {
     // ==================================================================== epilogue
     const int q = warp & 3;
@@ -400,8 +423,9 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t img_u = (uint32_t)tile / tpi, rem = (uint32_t)tile - img_u * tpi;
       const uint32_t ty_u = rem / (uint32_t)p.tiles_x;
       const int img = (int)img_u, ty = (int)ty_u, tx = (int)(rem - ty_u * (uint32_t)p.tiles_x);
-      const int as = iter & (acc_stages - 1);
-      const uint32_t accphase = (iter >> acc_shift) & 1;
+      int as;
+      uint32_t accphase;
+      ring_of(iter, acc_stages, p.acc_shift, as, accphase);
       const long long tw = p.dbg ? clock64() : 0;
       mbar_wait(&tmem_full[as], accphase, 4);
       if (p.dbg) t_wacc += clock64() - tw;
@@ -747,16 +771,39 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
   const int b_bytes = pair ? tc_stage_b_bytes(w) / 2 : tc_stage_b_bytes(w);   // per CTA
   const int stage_bytes = (L.mode == C8_HALO ? 0 : L.a_bytes) + (L.resident ? 0 : b_bytes);
   int fixed = (L.resident ? p.wres_bytes : 0);
+  // ---- rings and MMA issuers. Powers of two by default; a resident layer with nothing streamed per k-step (one short burst
+  // of small-N MMAs per tile) is bound by the ISSUE side - every UTCHMMA operand reaches the uniform registers through R2UR
+  // moves, ~130 cycles per MMA per issuing warp against 40-56 cycles of pipe time (ncu: tensor pipe 35 % active on the
+  // stems with two issuers) - so it gets THREE issuer warps (1, 3 and, after its allocation duty, the TMEM warp 2) and rings of
+  // 6 / 3 slots (an issuer count must divide every ring it indexes: a slot is then always handled by the same warp, in order)
+  static const int niss_cap = getenv("SE_C8_NISS") ? atoi(getenv("SE_C8_NISS")) : 3;   // A/B switch for experiments
   p.a_bufs = 2;
+  p.niss = 1;
+  p.acc_stages = w.NT <= 64 ? 8 : (w.NT <= 128 ? 4 : 2);
+  p.epi_split = w.NT <= 128 ? 1 : TC_EPI_GROUPS;
   if (L.mode == C8_HALO) {
     if (fixed + 2 * L.a_bytes + 3 * stage_bytes > smem_budget) p.a_bufs = 1;   // measured: 2 halo buffers + 3 weight stages beats 1 + 4
     // nothing streamed: a tile is short (700-2000 cycles of MMAs) against a TMA round trip of ~1500 cycles, so two
-    // halo buffers leave the tensor pipe waiting for loads; ring as deep as shared memory allows (power of two)
-    if (stage_bytes == 0)
-      while (p.a_bufs < C8_MAX_ABUFS && fixed + 2 * p.a_bufs * L.a_bytes <= smem_budget) p.a_bufs *= 2;
+    // halo buffers leave the tensor pipe waiting for loads; ring as deep as shared memory allows
+    if (stage_bytes == 0) {
+      if (!grp && !pair && niss_cap >= 3 && w.NT <= 128 && fixed + 3 * L.a_bytes <= smem_budget) {
+        p.niss = 3;
+        p.a_bufs = (fixed + 6 * L.a_bytes <= smem_budget) ? 6 : 3;
+        p.acc_stages = w.NT <= 64 ? 6 : 3;
+      } else {
+        while (p.a_bufs < C8_MAX_ABUFS && fixed + 2 * p.a_bufs * L.a_bytes <= smem_budget) p.a_bufs *= 2;
+        p.niss = (p.a_bufs % 2 == 0 && niss_cap >= 2) ? 2 : 1;
+      }
+    }
     fixed += p.a_bufs * L.a_bytes;
   }
-  for (p.a_shift = 0; (1 << p.a_shift) < p.a_bufs; ++p.a_shift) {}
+  p.acc_stride = w.NT <= 64 ? 64 : (w.NT <= 128 ? 128 : 256);
+  p.a_shift = -1;
+  for (int sh = 0; sh < 4; ++sh) if ((1 << sh) == p.a_bufs) p.a_shift = sh;
+  p.acc_shift = -1;
+  for (int sh = 0; sh < 4; ++sh) if ((1 << sh) == p.acc_stages) p.acc_shift = sh;
+  SE_REQUIRE(p.acc_stages * p.acc_stride <= TC_TMEM_COLS && p.a_bufs <= C8_MAX_ABUFS && p.a_bufs % p.niss == 0 && p.acc_stages % p.niss == 0,
+             "ring / issuer plan");
   SE_REQUIRE(!grp || (p.a_bufs >= 2 && w.NT <= 128 && p.ksteps == 1), "fused classes need two halo buffers, <= 128 accumulator columns and a single k-step");
   int stages = stage_bytes ? (smem_budget - fixed) / stage_bytes : 1;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;

@@ -225,6 +225,8 @@ struct se_model {
   std::vector<GraphEntry> graphs;
   std::map<std::vector<uintptr_t>, int> seen;
   unsigned long long tick = 0;
+  cudaStream_t gstream = nullptr;          // graphs cannot be captured on / launched into the legacy default stream: callers that pass it
+  cudaEvent_t bridge_in = nullptr, bridge_out = nullptr;   // (torch's default) are bridged through this stream with two events
   int device = -1;
   cudaStream_t last_stream = nullptr;
   bool used = false;
@@ -1175,13 +1177,35 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
   }
   // ---- replay a captured forward
   const bool graphable = g_graphs_on && !g_timing && !key.empty() && getenv("SE_TC_DEBUG") == nullptr && getenv("SE_DEBUG_NAN") == nullptr;
+  const bool legacy = (stream == nullptr || stream == cudaStreamLegacy);
+  cudaStream_t gs = stream;   // stream the graph is captured on / launched into
+  if (graphable && legacy) {
+    if (!m->gstream) {
+      SE_CUDA_OK(cudaStreamCreateWithFlags(&m->gstream, cudaStreamNonBlocking));
+      SE_CUDA_OK(cudaEventCreateWithFlags(&m->bridge_in, cudaEventDisableTiming));
+      SE_CUDA_OK(cudaEventCreateWithFlags(&m->bridge_out, cudaEventDisableTiming));
+    }
+    gs = m->gstream;
+  }
+  auto bridge_in = [&]() -> int {
+    if (gs != stream) { SE_CUDA_OK(cudaEventRecord(m->bridge_in, stream)); SE_CUDA_OK(cudaStreamWaitEvent(gs, m->bridge_in, 0)); }
+    return 0;
+  };
+  auto bridge_out = [&]() -> int {
+    if (gs != stream) { SE_CUDA_OK(cudaEventRecord(m->bridge_out, gs)); SE_CUDA_OK(cudaStreamWaitEvent(stream, m->bridge_out, 0)); }
+    return 0;
+  };
   if (graphable) {
     for (int k = 0; k < 8; ++k) key.push_back((uintptr_t)m->opt[k]);
     key.push_back((uintptr_t)prec);
     key.push_back((uintptr_t)B);
     for (auto& g : m->graphs)
       if (g.exec && g.arena == m->arena && g.key == key) {
-        SE_CUDA_OK(cudaGraphLaunch(g.exec, stream));
+        int rb = bridge_in();
+        if (rb) return rb;
+        SE_CUDA_OK(cudaGraphLaunch(g.exec, gs));
+        rb = bridge_out();
+        if (rb) return rb;
         g.tick = ++m->tick;
         g_launches = g.launches;
         return 0;
@@ -1196,7 +1220,10 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
   const size_t need = c.arena.peak + 4096;
   if (need > m->arena_bytes) {
     SE_CUDA_OK(cudaDeviceSynchronize());   // every stream that ever used the old slab
-    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);   // captured on the old slab
+    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (m->gstream) cudaStreamDestroy(m->gstream);
+  if (m->bridge_in) cudaEventDestroy(m->bridge_in);
+  if (m->bridge_out) cudaEventDestroy(m->bridge_out);   // captured on the old slab
     m->graphs.clear();
     if (m->arena) SE_CUDA_OK(cudaFree(m->arena));
     m->arena = nullptr;
@@ -1211,9 +1238,13 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
   // one-time initialisations - function attributes, driver entry points - that must not happen inside a capture)
   if (graphable && m->seen[key]++ >= 1) {
     cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    int rb = bridge_in();
+    if (rb) return rb;
+    if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      c.stream = gs;
       rc = fn(c);
-      const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+      c.stream = stream;
+      const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
       cudaGraphExec_t exec = nullptr;
       if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
         cudaGraphDestroy(graph);
@@ -1226,8 +1257,8 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
         se_model::GraphEntry e;
         e.key = key; e.exec = exec; e.arena = m->arena; e.launches = g_launches; e.tick = ++m->tick;
         m->graphs.push_back(e);
-        SE_CUDA_OK(cudaGraphLaunch(exec, stream));
-        return 0;
+        SE_CUDA_OK(cudaGraphLaunch(exec, gs));
+        return bridge_out();
       }
       if (graph) cudaGraphDestroy(graph);
       (void)cudaGetLastError();
@@ -1235,7 +1266,12 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
       if (rc) return rc;
       c.arena.reset((char*)m->arena);
       g_launches = 0;
+    } else {
+      (void)cudaGetLastError();  // a failed cudaStreamBeginCapture leaves a sticky error behind
+      m->seen[key] = -1000000;
     }
+    rb = bridge_out();           // (orders nothing new, but keeps the two streams' event pairs balanced)
+    if (rb) return rb;
   }
   return fn(c);
 }
@@ -1313,6 +1349,9 @@ void se_model_destroy(se_model* m) {
   if (m->arena) cudaFree(m->arena);
   if (m->order_ev) cudaEventDestroy(m->order_ev);
   for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (m->gstream) cudaStreamDestroy(m->gstream);
+  if (m->bridge_in) cudaEventDestroy(m->bridge_in);
+  if (m->bridge_out) cudaEventDestroy(m->bridge_out);
   delete m;
 }
 
