@@ -112,7 +112,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // warp-uniform by construction (a shuffle from lane 0): lets the compiler keep role-dependent values - the tile
   // parity of the second MMA issuer, ring indices, descriptors - on the uniform datapath
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int warp = uniform_warp_index();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -466,6 +466,27 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------ host
+void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
+  e->y = c.y; e->out_dt = c.out_dt; e->out_c8 = c.out_c8;
+  e->Hout = c.Hout; e->Wout = c.Wout; e->ldo = c.ldo; e->choff = c.choff;
+  e->osy = c.osy; e->ooy = c.ooy; e->osx = c.osx; e->oox = c.oox;
+  e->epi = c.epi; e->scale = c.scale; e->colscale = c.colscale;
+  e->Cout = c.Cout; e->NT = NT;
+  e->has_bias = c.bias != nullptr ? 1 : 0;
+  e->blk_split = c.out_blk_split > 0 ? c.out_blk_split : (1 << 20);
+  e->blk_jump = c.out_blk_split > 0 ? c.out_blk_jump : 0;
+  e->par_stride = c.out_par_stride > 0 ? c.out_par_stride : (c.ldo >> 2);
+  e->nsplit = c.f16x2 ? 2 : 1;
+  e->split_stride = (int)c.out_split_stride;
+  e->goff = (c.epi == EPI_LINEAR) ? 0 : gated_goff(c.Cout);
+}
+// the fast epilogue addresses the output in 32-bit units of 16 B
+static inline bool epi_out_fits_u32(const ConvParams& c) {
+  const double units = c.out_c8 ? (double)c.N * c.ldo * c.Hout * c.Wout : (double)c.N * c.Hout * c.Wout * c.ldo / 8.0;
+  return units < 4294967296.0 && (reinterpret_cast<uintptr_t>(c.y) & 15) == 0;
+}
+bool epi_addressable(const ConvParams& c) { return epi_out_fits_u32(c); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -776,7 +797,10 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
   // moves, ~130 cycles per MMA per issuing warp against 40-56 cycles of pipe time (ncu: tensor pipe 35 % active on the
   // stems with two issuers) - so it gets THREE issuer warps (1, 3 and, after its allocation duty, the TMEM warp 2) and rings of
   // 6 / 3 slots (an issuer count must divide every ring it indexes: a slot is then always handled by the same warp, in order)
-  static const int niss_cap = getenv("SE_C8_NISS") ? atoi(getenv("SE_C8_NISS")) : 3;   // A/B switch for experiments
+  // (three issuers need rings of 3 / 6 slots, which the FOUR tile-alternating epilogue groups do not divide: a TMEM stage is then
+  //  drained by changing groups and a group can test its full-barrier a whole phase early - parity waits alias modulo 2 - so this
+  //  stays an experiment switch, default two issuers)
+  static const int niss_cap = getenv("SE_C8_NISS") ? atoi(getenv("SE_C8_NISS")) : 2;
   p.a_bufs = 2;
   p.niss = 1;
   p.acc_stages = w.NT <= 64 ? 8 : (w.NT <= 128 ? 4 : 2);

@@ -1,4 +1,5 @@
-// Host/device interface of the tcgen05 convolution (se_conv_tc.cu).
+// Weight stage images of the tcgen05 convolution (se_conv_c8.cu): the swizzled shared-memory layout shared by the packer
+// (se_engine.cu) and the kernel.
 #pragma once
 #include "se_common.cuh"
 
@@ -39,27 +40,7 @@ __host__ __device__ inline uint32_t tc_b_image_offset(int NT, int r64, bool is64
   return (uint32_t)r64 * NT * 128 + (uint32_t)j * NT * 64 + tc_swizzle_offset(n, k * 2, 64);
 }
 
-struct TcParams {
-  int N, Ho, Wo;
-  int tiles_x, tiles_y, n_tiles;
-  int stride;
-  int ntaps;
-  int8_t dy[MAX_TAPS], dx[MAX_TAPS];
-  int n64, n32, r64, r32, NT;
-  int ksteps;
-  long long w_img_bytes;
-  const uint8_t* w;
-  int num_stages;
-  const float* bias;
-  EpiParams e;
-  unsigned long long* dbg;   // optional per-CTA role timers (SE_TC_DEBUG=1)
-};
-
-// pick (r64, r32) for a layer: as many units per stage as fit ~48 KB (SE_TC_STAGE_KB)
-void tc_choose_stage(TcWeights* w);
 void fill_epi(const ConvParams& c, int NT, EpiParams* e);
 bool epi_addressable(const ConvParams& c);   // output fits the fast epilogue's 32-bit (16 B unit) addressing
-int tc_plan(const ConvParams& c, const TcWeights& w, TcParams* out, int* smem_bytes);
-int tc_launch(const ConvParams& c, const TcWeights& w, cudaStream_t stream);
 
 }  // namespace se

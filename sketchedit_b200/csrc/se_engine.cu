@@ -169,7 +169,6 @@ struct ClassW {
   int8_t dy[MAX_TAPS], dx[MAX_TAPS];
   float* w_direct = nullptr;   // device fp32 [tap][Ci][CoutP]
   int CoutP = 0;
-  TcWeights tc;                // device bf16 (se_conv_tc.cu: NHWC input; stride-2 layers and attention)
   bool has_tc = false;
   C8Layer c8;                  // se_conv_c8.cu: channel-blocked input (every stride-1 layer on the bf16 path)
   bool use_c8 = false;
@@ -300,24 +299,12 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
         cw.c8cb[t] = (int8_t)((py * 2 + px) * (Ci / 8));
       }
     }
-    TcWeights* tcp;
-    if (cw.use_c8) {
+    SE_REQUIRE(cw.use_c8, "layer " + L.name + " has no tensor-core form");   // every gated layer of the two generators has one
+    {
       int rc = c8_configure(&cw.c8, cw.ntaps, cw.c8dy, cw.c8dx, Ci, Cout, L.is_stem, cw.c8cb);
       if (rc) return rc;
-      tcp = &cw.c8.w;
-    } else {
-      TcWeights& tc = cw.tc;
-      tc.ntaps = cw.ntaps;
-      tc.n64 = Ci / 64;
-      int rem = Ci - 64 * tc.n64;
-      if (rem > 32) { ++tc.n64; rem = 0; }
-      tc.n32 = rem > 0 ? 1 : 0;
-      tc.NT = (gated_goff(Cout) + Cout / 2 + 15) / 16 * 16;   // gate columns start at goff (se_common.cuh: gated_column)
-      tc.n_tiles = 1;
-      tc.img_bytes = 0;
-      tc_choose_stage(&tc);
-      tcp = &tc;
     }
+    TcWeights* tcp = &cw.c8.w;
     // the exact (swizzled) shared-memory image of every pipeline stage, see se_conv_tc.h. Gate channels (n >= Cout/2) are stored
     // pre-multiplied by 0.5 (exact): the accumulator then holds 0.5*g and the epilogue's sigmoid(g + b) = 0.5*tanh(0.5*g + 0.5*b) + 0.5
     // needs one add (with a constant operand) before the MUFU
@@ -598,7 +585,7 @@ static Layer* find_ready(se_model* m, char net, const std::string& name) {
 
 static int launch_conv(Ctx& c, const ConvParams& cp, const ClassW& cw) {
   if (c.split() && cw.has_split) return c8_launch(cp, cw.c8s, c.stream);
-  if (c.prec == SE_PREC_BF16_TC && cw.has_tc) return cw.use_c8 ? c8_launch(cp, cw.c8, c.stream) : tc_launch(cp, cw.tc, c.stream);
+  if (c.prec == SE_PREC_BF16_TC && cw.has_tc) return c8_launch(cp, cw.c8, c.stream);
   ConvParams d = cp;
   d.w = cw.w_direct;
   return direct_launch(d, cw.CoutP, c.prec == SE_PREC_FP32_EXACT, c.stream);
@@ -696,7 +683,7 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
       const double bytes = ((double)c.B * in.H * in.W * (L.fused_pair ? 8.0 : (double)s.cin) / ncls + pos * (s.cout / 2) + (double)s.cout * s.cin * s.k * s.k / ncls) * c.esz();
       const bool tcp = c.tc() && cw.has_tc;
       char buf[160];
-      snprintf(buf, sizeof(buf), "%s|%s %d->%d k%d s%d d%d @%dx%d", tcp ? (split ? "conv_c8_kernel (split-half fp16 x3)" : cw.use_c8 ? "conv_c8_kernel" : "conv_tc_kernel") : "conv_direct_kernel",
+      snprintf(buf, sizeof(buf), "%s|%s %d->%d k%d s%d d%d @%dx%d", tcp ? (split ? "conv_c8_kernel (split-half fp16 x3)" : "conv_c8_kernel") : "conv_direct_kernel",
                s.deconv ? (grp ? (grp->ncls == 4 ? "deconv (4 classes fused)" : "deconv (2 classes fused)") : "deconv-class") : (L.fused_pair ? "stem pair" : "conv"), s.cin, s.cout, s.k, s.stride, s.rate, Ho * cw.osy, Wo * cw.osx);
       c.tag(buf, tcp ? 1 : 0, f_alg, f_exec, bytes);
     }
@@ -833,7 +820,8 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   SE_REQUIRE(h % 2 == 0 && w % 2 == 0 && h >= 4 && w >= 4, "attention map must be even-sized and >= 4");
   const int hs = (h - 4) / 2 + 1, ws = (w - 4) / 2 + 1, L = hs * ws;
   const int Lpad = (L + 127) / 128 * 128;
-  const bool tc = (c.prec == SE_PREC_BF16_TC) && (C % 32 == 0) && (f.ld % 8 == 0);
+  // CUDA-core path (fp32 modes, the bf16 cross-check, and channel counts other than netG's 96): the tensor-core attention is
+  // run_cam_tc / se_cam.cu
   const int dt = c.act_dt();
 
   Buf rnorm = c.get((size_t)B * C * 4);
@@ -844,16 +832,11 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   CK(cam_colmask(mask_s, (float*)colm.p, B, h, w, hs, ws, 0.1f, c.stream));
 
   // ---- keys
-  TcWeights ktc;   // S = Q K^T: 16 taps of C channels, N tiles of 128 keys
-  ktc.ntaps = 16; ktc.n64 = C / 64; ktc.n32 = (C % 64) ? 1 : 0; ktc.NT = 128; ktc.n_tiles = Lpad / 128;
-  tc_choose_stage(&ktc);
-  ktc.img_bytes = tc ? tc_weight_bytes_per_image(ktc) : 0;
-  const size_t kbytes = tc ? (size_t)B * ktc.img_bytes : (size_t)B * 16 * C * Lpad * 4;
+  const size_t kbytes = (size_t)B * 16 * C * Lpad * 4;   // keys as per-image conv kernels: fp32 [b][tap][c][Lpad]
   Buf kbuf = c.get(kbytes);
   SE_REQUIRE(f.ld == C, "attention input must be dense NHWC");
-  SE_REQUIRE(!tc || (C % 32 == 0 && (C % 64 == 0 || C % 64 == 32)), "attention channel count");
   c.tag("cam_pack_k|attention key operand", 0, 0, 0, (double)B * h * w * C * c.esz() + (double)kbytes);
-  CK(cam_pack_k(f.p, dt, (const float*)rnorm.p, kbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, ktc.r64, ktc.r32, c.stream));
+  CK(cam_pack_k(f.p, dt, (const float*)rnorm.p, kbuf.p, B, h, w, C, ws, L, Lpad, c.stream));
 
   // ---- logits S[b, n, l] (fp32, row pitch Lpad), scaled by 10 * m_l in the GEMM epilogue
   Buf sbuf = c.get((size_t)B * L * Lpad * 4);
@@ -871,11 +854,8 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cw.ntaps = 16;
     cw.CoutP = Lpad;
     cw.w_direct = (float*)kbuf.p;
-    cw.has_tc = tc;
-    cw.tc = ktc;
-    cw.tc.data = kbuf.p;
     cp.w_img_stride = (long long)16 * C * Lpad;
-    c.tag(tc ? "conv_tc_kernel|attention S=QK^T" : "conv_direct_kernel|attention S=QK^T", tc ? 1 : 0, 2.0 * B * L * (double)L * C * 16,
+    c.tag("conv_direct_kernel|attention S=QK^T", 0, 2.0 * B * L * (double)L * C * 16,
           2.0 * B * L * (double)L * C * 16, (double)B * h * w * C * c.esz() + (double)kbytes + (double)B * L * Lpad * 4);
     CK(launch_conv(c, cp, cw));
   }
@@ -896,14 +876,10 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   c.put(colm);
 
   // ---- values + fold-sum
-  TcWeights vtc;   // out = P V per sub-pixel class: 4 taps of Lpad "channels" (keys), N = C
-  vtc.ntaps = 4; vtc.n64 = Lpad / 64; vtc.n32 = 0; vtc.NT = (C + 15) / 16 * 16; vtc.n_tiles = 1;
-  tc_choose_stage(&vtc);
-  vtc.img_bytes = tc_weight_bytes_per_image(vtc);
-  const size_t per_pc_bytes = tc ? (size_t)B * vtc.img_bytes : (size_t)B * 4 * Lpad * C * 4;
+  const size_t per_pc_bytes = (size_t)B * 4 * Lpad * C * 4;   // values per sub-pixel class: fp32 [b][tap][key][c]
   Buf vbuf = c.get(4 * per_pc_bytes);
   c.tag("cam_pack_v|attention value operand", 0, 0, 0, (double)B * h * w * C * c.esz() + 4.0 * per_pc_bytes);
-  CK(cam_pack_v(f.p, dt, vbuf.p, tc ? 1 : 0, B, h, w, C, ws, L, Lpad, vtc.r64, (long long)per_pc_bytes, c.stream));
+  CK(cam_pack_v(f.p, dt, vbuf.p, B, h, w, C, ws, L, Lpad, c.stream));
   for (int pc = 0; pc < 4; ++pc) {
     ConvParams cp;
     memset(&cp, 0, sizeof(cp));
@@ -919,11 +895,8 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
     cw.ntaps = 4;
     cw.CoutP = C;
     cw.w_direct = reinterpret_cast<float*>((char*)vbuf.p + pc * per_pc_bytes);
-    cw.has_tc = tc;
-    cw.tc = vtc;
-    cw.tc.data = (const char*)vbuf.p + pc * per_pc_bytes;
     cp.w_img_stride = (long long)4 * Lpad * C;
-    c.tag(tc ? "conv_tc_kernel|attention out=fold(PV) class" : "conv_direct_kernel|attention out=fold(PV) class", tc ? 1 : 0,
+    c.tag("conv_direct_kernel|attention out=fold(PV) class", 0,
           2.0 * B * (h / 2) * (w / 2) * (double)C * L * 4, 2.0 * B * (h / 2) * (w / 2) * (double)C * L * 4,
           ((double)B * L * Lpad + (double)B * 4 * Lpad * C + (double)B * (h / 2) * (w / 2) * C) * c.esz());
     CK(launch_conv(c, cp, cw));

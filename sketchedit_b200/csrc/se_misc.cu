@@ -3,7 +3,6 @@
 // conversion. All activations are NHWC; T is the activation storage type (bf16 fast path / fp32 exact).
 #include "se_common.cuh"
 #include "se_misc.h"
-#include "se_conv_tc.h"
 
 namespace se {
 
@@ -504,43 +503,6 @@ int cam_colmask(const float* mask_s, float* out, int B, int h, int w, int hs, in
 
 // ------------------------------------------------------------------------------------------ attention operands
 // Keys  K[l][(u,v,c)] = f[2ly+u, 2lx+v, c] * rnorm[c]        (splitcam.py:39-44, norm_type 1, 4x4 / stride 2)
-// tcgen05 layout: per image, per 128-key tile, per stage the swizzled B image (se_conv_tc.h), 16 taps of C channels
-template <typename T>
-__global__ void cam_pack_k_tc_kernel(const T* __restrict__ f, const float* __restrict__ rnorm, uint8_t* __restrict__ out,
-                                     int B, int h, int w, int C, int ws, int L, int Lpad, int r64, int r32, long long total) {
-  // one thread = 8 consecutive channels (one 16 B swizzle chunk) of one key pixel and tap
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int C8n = C >> 3;
-  const int co = (int)(i % C8n);
-  long long r = i / C8n;
-  const int l = (int)(r % Lpad); r /= Lpad;
-  const int tap = (int)(r % 16);
-  const long long b = r / 16;
-  const int c = co * 8;
-  float v[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = 0.0f;
-  if (l < L) {
-    const int ly = l / ws, lx = l % ws, u = tap / 4, vv = tap % 4;
-    const T* src = f + ((b * h + 2 * ly + u) * w + 2 * lx + vv) * C + c;
-    const float* rn = rnorm + b * C + c;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = to_f<T>(src[k]) * rn[k];
-  }
-  const int NT = 128, n64 = C / 64;
-  const int ksteps = n64 ? 16 * n64 / r64 : 16 / r32;
-  const int sb = NT * (r64 * 128 + r32 * 64);
-  const int nt = l / NT, n = l % NT;
-  int ks, j, k0;
-  const bool is64 = c < n64 * 64;
-  if (is64) { const int uu = tap * n64 + c / 64; ks = uu / r64; j = uu % r64; k0 = c % 64; }
-  else { ks = tap / r32; j = tap % r32; k0 = c - n64 * 64; }
-  const size_t img_bytes = (size_t)(Lpad / NT) * ksteps * sb;
-  uint8_t* dst = out + (size_t)b * img_bytes + ((size_t)nt * ksteps + ks) * sb + tc_b_image_offset(NT, n64 ? r64 : 0, is64, j, n, k0);
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
-
 // direct layout: fp32 [b][tap][c][CoutP]
 template <typename T>
 __global__ void cam_pack_k_direct_kernel(const T* __restrict__ f, const float* __restrict__ rnorm, float* __restrict__ out,
@@ -560,16 +522,9 @@ __global__ void cam_pack_k_direct_kernel(const T* __restrict__ f, const float* _
   out[i] = v;
 }
 
-int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L,
-               int Lpad, int r64, int r32, cudaStream_t s) {
+int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int B, int h, int w, int C, int ws, int L, int Lpad, cudaStream_t s) {
   const long long total = (long long)B * 16 * C * Lpad;
-  if (tc_layout) {
-    SE_REQUIRE(C % 32 == 0 && Lpad % 128 == 0, "C % 32, Lpad % 128");
-    const long long chunks = total / 8;
-    SE_DISPATCH_T(dt, (cam_pack_k_tc_kernel<T><<<cdiv(chunks, 256), 256, 0, s>>>((const T*)f, rnorm, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, r32, chunks)));
-  } else {
-    SE_DISPATCH_T(dt, (cam_pack_k_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (float*)out, B, h, w, C, ws, L, Lpad, total)));
-  }
+  SE_DISPATCH_T(dt, (cam_pack_k_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, rnorm, (float*)out, B, h, w, C, ws, L, Lpad, total)));
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -577,80 +532,6 @@ int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layo
 // Values for the fold-sum written as 4 sub-pixel (parity) 2x2 "convolutions" over the token image
 // P[b, ny, nx, l] (splitcam.py:152, utils.py:102-128):
 //   out[2yy+py, 2xx+px, c] = sum_{a,b in {0,1}} sum_l P[yy-a, xx-b, l] * f[2ly+py+2a, 2lx+px+2b, c]
-// tcgen05 layout: per sub-pixel class pc, per image, per stage the swizzled B image: K = (tap, key l) in 64-wide
-// units, N = channel c
-template <typename T>
-__global__ void cam_pack_v_tc_kernel(const T* __restrict__ f, uint8_t* __restrict__ out, int B, int h, int w, int C, int ws,
-                                     int L, int Lpad, int r64, long long pc_bytes, long long total) {
-  // one thread = 8 consecutive keys (one 16 B swizzle chunk) of one channel row; the 8 chunks of a 128 B row are
-  // written by 8 adjacent threads
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int lo = (int)(i % (Lpad >> 3));
-  long long r = i / (Lpad >> 3);
-  const int c = (int)(r % C); r /= C;
-  const int tap = (int)(r % 4); r /= 4;
-  const long long b = r % B;
-  const int pc = (int)(r / B);
-  const int py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
-  float v[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int l = lo * 8 + k;
-    v[k] = 0.0f;
-    if (l < L) {
-      const int ly = l / ws, lx = l % ws;
-      v[k] = to_f<T>(f[((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + c]);
-    }
-  }
-  const int NT = (C + 15) / 16 * 16, n64 = Lpad / 64;
-  const int ksteps = 4 * n64 / r64, sb = NT * r64 * 128;
-  const int l0 = lo * 8;
-  const int u = tap * n64 + l0 / 64, ks = u / r64, j = u % r64;
-  uint8_t* dst = out + (size_t)pc * pc_bytes + (size_t)b * ((size_t)ksteps * sb) + (size_t)ks * sb + tc_b_image_offset(NT, r64, true, j, c, l0 % 64);
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
-
-// Same image, bf16 input, built through shared memory: a block owns one (class, image, tap, 64-key unit); it reads
-// the 64 key pixels as contiguous channel vectors (coalesced 16 B loads; the kernel above reads 2 B at a 2-pixel
-// stride per key, a full sector per element), transposes in shared memory and writes whole 16 B swizzle chunks.
-__global__ void __launch_bounds__(256) cam_pack_v_tc_tile_kernel(const __nv_bfloat16* __restrict__ f, uint8_t* __restrict__ out, int B, int h, int w,
-                                                                 int C, int ws, int L, int Lpad, int r64, long long pc_bytes) {
-  constexpr int PITCH = 128 + 8;                       // bf16 elements per key row (C <= 128), 16 B aligned, odd multiple of 16 B
-  __shared__ __align__(16) __nv_bfloat16 tile[64][PITCH];
-  const int u64 = blockIdx.x, tap = blockIdx.y;
-  const int pc = blockIdx.z / B;
-  const long long b = blockIdx.z % B;
-  const int py = pc / 2, px = pc % 2, a = tap / 2, bb = tap % 2;
-  const int C8n = C >> 3;
-  for (int idx = threadIdx.x; idx < 64 * C8n; idx += 256) {
-    const int key = idx / C8n, ch = idx - key * C8n;
-    const int l = u64 * 64 + key;
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (l < L) {
-      const int ly = l / ws, lx = l - ly * ws;
-      q = *reinterpret_cast<const uint4*>(f + ((b * h + 2 * ly + py + 2 * a) * w + 2 * lx + px + 2 * bb) * C + ch * 8);
-    }
-    *reinterpret_cast<uint4*>(&tile[key][ch * 8]) = q;
-  }
-  __syncthreads();
-  const int NT = (C + 15) / 16 * 16, n64 = Lpad / 64;
-  const int ksteps = 4 * n64 / r64, sb = NT * r64 * 128;
-  const int u = tap * n64 + u64, ks = u / r64, j = u % r64;
-  uint8_t* base = out + (size_t)pc * pc_bytes + (size_t)b * ((size_t)ksteps * sb) + (size_t)ks * sb;
-  for (int idx = threadIdx.x; idx < C * 8; idx += 256) {
-    const int kc = idx & 7, c = idx >> 3;              // 8 key chunks of one channel row = one 128 B row of the image
-    uint32_t wds[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t lo = *reinterpret_cast<const uint16_t*>(&tile[kc * 8 + 2 * k][c]);
-      const uint32_t hi = *reinterpret_cast<const uint16_t*>(&tile[kc * 8 + 2 * k + 1][c]);
-      wds[k] = lo | (hi << 16);
-    }
-    *reinterpret_cast<uint4*>(base + tc_b_image_offset(NT, r64, true, j, c, kc * 8)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-  }
-}
-
 // direct layout: fp32 [pc][b][tap][l (Ci = Lpad)][CoutP = C]
 template <typename T>
 __global__ void cam_pack_v_direct_kernel(const T* __restrict__ f, float* __restrict__ out, int B, int h, int w, int C, int ws, int L,
@@ -671,21 +552,9 @@ __global__ void cam_pack_v_direct_kernel(const T* __restrict__ f, float* __restr
   out[i] = v;
 }
 
-int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L, int Lpad, int r64,
-               long long pc_bytes, cudaStream_t s) {
+int cam_pack_v(const void* f, int dt, void* out, int B, int h, int w, int C, int ws, int L, int Lpad, cudaStream_t s) {
   const long long total = 4LL * B * 4 * Lpad * C;
-  if (tc_layout) {
-    SE_REQUIRE(Lpad % 64 == 0, "Lpad % 64");
-    if (C % 16) SE_CUDA_OK(cudaMemsetAsync(out, 0, 4 * pc_bytes, s));   // padded N rows
-    const long long chunks = total / 8;
-    if (dt == DT_BF16 && C % 8 == 0 && C <= 128 && 4LL * B <= 65535) {
-      cam_pack_v_tc_tile_kernel<<<dim3(Lpad / 64, 4, 4 * B), 256, 0, s>>>((const __nv_bfloat16*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes);
-    } else {
-      SE_DISPATCH_T(dt, (cam_pack_v_tc_kernel<T><<<cdiv(chunks, 256), 256, 0, s>>>((const T*)f, (uint8_t*)out, B, h, w, C, ws, L, Lpad, r64, pc_bytes, chunks)));
-    }
-  } else {
-    SE_DISPATCH_T(dt, (cam_pack_v_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (float*)out, B, h, w, C, ws, L, Lpad, total)));
-  }
+  SE_DISPATCH_T(dt, (cam_pack_v_direct_kernel<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)f, (float*)out, B, h, w, C, ws, L, Lpad, total)));
   SE_CUDA_OK(cudaGetLastError());
   return 0;
 }

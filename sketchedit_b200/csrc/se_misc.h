@@ -21,10 +21,8 @@ int plane_reduce(const void* x, int dt, int B, int HW, int C, int ldx, int c8, i
 int broadcast_channels(const float* v, void* y, int dt, int B, int HW, int C, int ldo, int choff, int c8, cudaStream_t s);
 int avgpool4(const float* m, float* out, int B, int H, int W, cudaStream_t s);
 int cam_colmask(const float* mask_s, float* out, int B, int h, int w, int hs, int ws, float th, cudaStream_t s);
-int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L,
-               int Lpad, int r64, int r32, cudaStream_t s);
-int cam_pack_v(const void* f, int dt, void* out, int tc_layout, int B, int h, int w, int C, int ws, int L, int Lpad, int r64,
-               long long pc_bytes, cudaStream_t s);
+int cam_pack_k(const void* f, int dt, const float* rnorm, void* out, int B, int h, int w, int C, int ws, int L, int Lpad, cudaStream_t s);
+int cam_pack_v(const void* f, int dt, void* out, int B, int h, int w, int C, int ws, int L, int Lpad, cudaStream_t s);
 int softmax_rows(const float* S, int lds, void* P, int dt, int ldp, long long rows, int L, cudaStream_t s);
 int nchw_to_stem8(const float* x, void* y, int dt, int B, int cin, int H, int W, int Wp, int padl, cudaStream_t s);
 int nchw_to_c8_s2d(const float* x, void* y, int B, int C, int H, int W, cudaStream_t s);

@@ -85,6 +85,17 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
+// warp index inside the CTA as a value the compiler KNOWS to be warp-uniform: built from vote results (a shuffle broadcast has
+// the same value but is not recognised as uniform, so everything inside the role branches stayed on the vector datapath and
+// every tcgen05.mma operand went through R2UR moves)
+__device__ __forceinline__ int uniform_warp_index() {
+  const int w = (int)(threadIdx.x >> 5);
+  int r = 0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) r |= __any_sync(0xffffffffu, (w >> k) & 1) ? (1 << k) : 0;
+  return r;
+}
+
 // one lane of a fully converged warp (the warp stays converged: the compiler keeps addresses / descriptors
 // in uniform registers instead of broadcasting them lane by lane)
 __device__ __forceinline__ bool elect_one() {
