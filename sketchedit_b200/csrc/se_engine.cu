@@ -1193,10 +1193,7 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
   const size_t need = c.arena.peak + 4096;
   if (need > m->arena_bytes) {
     SE_CUDA_OK(cudaDeviceSynchronize());   // every stream that ever used the old slab
-    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-  if (m->gstream) cudaStreamDestroy(m->gstream);
-  if (m->bridge_in) cudaEventDestroy(m->bridge_in);
-  if (m->bridge_out) cudaEventDestroy(m->bridge_out);   // captured on the old slab
+    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);   // captured on the old slab
     m->graphs.clear();
     if (m->arena) SE_CUDA_OK(cudaFree(m->arena));
     m->arena = nullptr;

@@ -19,57 +19,43 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug traps after ~2 s of wall time (%globaltimer) instead of hanging the GPU box.
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity, const char* what) {
-  printf("sketchedit_b200: %s timeout tag=%d block=%d thread=%d parity=%u\n", what, tag, blockIdx.x, threadIdx.x, parity);
-  __trap();
-}
+// Bounded wait: a protocol bug traps after ~2 s of wall time (%globaltimer) instead of hanging the GPU box. The whole loop is
+// ONE asm block on purpose: written as a C++ loop (per-lane `done` flag, early return, printf on timeout) ptxas treated
+// everything after a wait as possibly divergent, kept every later value in vector registers and fed each tcgen05.mma operand
+// through R2UR moves (4-7 per MMA; the stems' tensor pipe was 35 % active). (`tag` names the wait site; kept for debugging builds.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  uint64_t t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((it & 255u) == 255u) {
-      const uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity, "mbarrier");
-    }
-  }
+  (void)tag;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 t0, t1;\n\t"
+      "mov.u64 t0, %%globaltimer;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "mov.u64 t1, %%globaltimer;\n\t"
+      "sub.u64 t1, t1, t0;\n\t"
+      "setp.lt.u64 p, t1, 2000000000;\n\t"
+      "@p bra WAIT_%=;\n\t"
+      "trap;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // same, acquiring at cluster scope: the barrier is signalled by threads of the peer CTA (CTA pairs)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  uint64_t t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((it & 255u) == 255u) {
-      const uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) mbar_timeout(tag, parity, "cluster mbarrier");
-    }
-  }
+  (void)tag;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 t0, t1;\n\t"
+      "mov.u64 t0, %%globaltimer;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "mov.u64 t1, %%globaltimer;\n\t"
+      "sub.u64 t1, t1, t0;\n\t"
+      "setp.lt.u64 p, t1, 2000000000;\n\t"
+      "@p bra WAIT_%=;\n\t"
+      "trap;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
