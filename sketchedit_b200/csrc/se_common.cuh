@@ -113,6 +113,11 @@ struct EpiParams {
   int goff;   // gated epilogues: accumulator column of gate channel 0 (= Cout/2 rounded up to 8; the weight image
               // places feature c at column c and its gate at goff + c, columns in between are zero weights)
 };
+// Split-half tensors (DT_F16X2) store value * kSplitActScale: fp16's narrow exponent would otherwise push the lo half of every
+// activation below ~0.25 into the subnormals (quantum 2^-24: ~1e-6 relative at 0.03). Times 64 the pair keeps ~22 bits down to
+// |v| = 2^-9 and stays finite up to |v| = 1000 (saturating beyond). Weights are scaled per class by a power of two of their own
+// (ClassW::s_wscale); the epilogue multiplies the accumulator by 1 / (kSplitActScale * s_wscale) inside the bias FMA.
+constexpr float kSplitActScale = 64.0f, kSplitActInv = 1.0f / 64.0f, kSplitActMax = 65000.0f;
 // column of output channel n in the B (weight) image / accumulator of a gated layer
 inline int gated_goff(int Cout) { return ((Cout / 2) + 7) / 8 * 8; }
 inline int gated_column(int Cout, int n) { const int half = Cout / 2; return n < half ? n : gated_goff(Cout) + (n - half); }

@@ -7,6 +7,8 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cmath>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -183,6 +185,7 @@ struct ClassW {
   C8Layer c8s;
   bool has_split = false;
   int s_ntaps = 0;
+  float s_wscale = 1.0f;   // power of two the split-half weight images are multiplied by
   int8_t s_dy[MAX_TAPS], s_dx[MAX_TAPS], s_cb[MAX_TAPS];
 };
 
@@ -359,9 +362,18 @@ static int pack_class(se_model* m, Layer& L, const std::vector<EffTap>& taps, Cl
         }
       rc = c8_configure(&cw.c8s, cw.s_ntaps, cw.s_dy, cw.s_dx, Ci, Cout, L.is_stem, cw.s_cb);
       if (rc) return rc;
+      // weights times a power of two (exact) that brings the largest one to [8192, 16384): the lo halves of all but negligible
+      // weights are then normal fp16 numbers (22 bits for the pair); the epilogue undoes it (se_common.cuh: kSplitActScale)
+      float wmax = 0.0f;
+      for (int t = 0; t < cw.ntaps; ++t)
+        for (int ci = 0; ci < Ci; ++ci)
+          for (int n = 0; n < Cout; ++n) wmax = std::max(wmax, std::fabs(wval(t, ci, n)));
+      int kw = 0;
+      if (wmax > 0.0f && std::isfinite(wmax)) kw = std::min(24, std::max(0, 13 - (int)std::floor(std::log2(wmax))));
+      cw.s_wscale = std::ldexp(1.0f, kw);
       auto half_bits = [](float v) -> uint16_t { return __half_as_ushort(__float2half_rn(v)); };
       rc = build_images(cw.c8s.w, &cw.c8s, [&](int vt, int ci, int n) -> uint16_t {
-        const float w = wval(vt / 3, ci, n);
+        const float w = wval(vt / 3, ci, n) * cw.s_wscale;
         const float hi = __half2float(__float2half_rn(w));
         return (vt % 3) == 1 ? half_bits(w - hi) : half_bits(w);
       });
@@ -642,6 +654,7 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     if (split) {
       SE_REQUIRE(cw.has_split && in.c8 && out_c8, "split-half mode runs on channel-blocked activations (layer " + L.name + ")");
       cp.f16x2 = 1;
+      cp.scale = 1.0f / (kSplitActScale * cw.s_wscale);   // accumulator -> true pre-activation (exact: powers of two)
       // hi blocks first, lo blocks after them: per image (channel-blocked) or per parity group (space-to-depth)
       cp.out_split_stride = out_c8 == 2 ? (long long)(ldo / 8) * (Ho * cw.osy / 2) * (Wo * cw.osx / 2) : (long long)(ldo / 2) * (Ho * cw.osy) * (Wo * cw.osx);
     }
@@ -1401,7 +1414,7 @@ static int forward_inference(se_model* m, const float* image, const float* sketc
     const float* mbin = (const float*)mb.p;
     if (mask_bin_in) mbin = mask_bin_in;
     if (mask_bin_out && !c.dry) {
-      SE_CUDA_OK(cudaMemcpyAsync(mask_bin_out, mbin, (size_t)B * H * W * 4, cudaMemcpyDeviceToDevice, st));
+      SE_CUDA_OK(cudaMemcpyAsync(mask_bin_out, mbin, (size_t)B * H * W * 4, cudaMemcpyDeviceToDevice, c.stream));
     }
     // generate_fake: netG(inputs, inputs, mask_bin, mask_bin, line)   (editline2_model.py:368)
     r = run_netG(c, image, image, mbin, mbin, sketch, H, W, coarse, fine, composed, mask, image, composed_bs, mask_bs);
@@ -1438,7 +1451,7 @@ int se_forward_inference_u8(se_model* m, const unsigned char* image_u8, const un
     // (test.py:25-35): the float image / masks live only in the workspace
     Buf img = c.get((size_t)B * 3 * H * W * 4), sk = c.get((size_t)B * H * W * 4), soft = c.get((size_t)B * H * W * 4), mb = c.get((size_t)B * H * W * 4);
     c.tag("u8_to_inputs_kernel|input codec", 0, 0, 0, (double)B * H * W * (4 + 16));
-    CK(u8_to_inputs(image_u8, sketch_u8, (float*)img.p, (float*)sk.p, B, H, W, st));
+    CK(u8_to_inputs(image_u8, sketch_u8, (float*)img.p, (float*)sk.p, B, H, W, c.stream));
     int r = run_netM(c, (const float*)img.p, (const float*)sk.p, H, W, (float*)soft.p, nullptr, (float*)mb.p, 0, mask_u8);
     if (r) return r;
     r = run_netG(c, (const float*)img.p, (const float*)img.p, (const float*)mb.p, (const float*)mb.p, (const float*)sk.p, H, W, nullptr, nullptr, nullptr,
@@ -1484,18 +1497,18 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
     Buf in = c.get(L->is_stem ? (size_t)B * H * stem_wp(W) * 8 * c.esz() : act_bytes(c, H, W, Ci, in_c8));
     if (c.split()) {
       // split-half storage: hi / lo fp16 halves of the fp32 input in the layout the layer reads
-      if (L->is_stem || s.cin % 8) CK(fill_zero(in.p, in.bytes, st));
-      CK(nchw_to_split(x, in.p, B, s.cin, H, W, L->is_stem ? 3 : in_c8, stem_wp(W), STEM_PADL, st));
+      if (L->is_stem || s.cin % 8) CK(fill_zero(in.p, in.bytes, c.stream));
+      CK(nchw_to_split(x, in.p, B, s.cin, H, W, L->is_stem ? 3 : in_c8, stem_wp(W), STEM_PADL, c.stream));
     } else if (L->is_stem) {
-      CK(fill_zero(in.p, in.bytes, st));
-      CK(nchw_to_stem8(x, in.p, dt, B, s.cin, H, W, stem_wp(W), STEM_PADL, st));
+      CK(fill_zero(in.p, in.bytes, c.stream));
+      CK(nchw_to_stem8(x, in.p, dt, B, s.cin, H, W, stem_wp(W), STEM_PADL, c.stream));
     } else if (in_c8 == 2) {
-      CK(nchw_to_c8_s2d(x, in.p, B, s.cin, H, W, st));
+      CK(nchw_to_c8_s2d(x, in.p, B, s.cin, H, W, c.stream));
     } else if (in_c8) {
-      if (s.cin % 8) CK(fill_zero(in.p, in.bytes, st));
-      CK(nchw_to_c8(x, in.p, B, s.cin, H * W, st));
+      if (s.cin % 8) CK(fill_zero(in.p, in.bytes, c.stream));
+      CK(nchw_to_c8(x, in.p, B, s.cin, H * W, c.stream));
     } else {
-      CK(nchw_to_nhwc(x, in.p, dt, B, s.cin, H * W, Ci, 0, st));
+      CK(nchw_to_nhwc(x, in.p, dt, B, s.cin, H * W, Ci, 0, c.stream));
     }
     int Ho, Wo;
     out_dims(s, H, W, &Ho, &Wo);
@@ -1512,8 +1525,8 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
       cp.w = cw.w_direct; cp.bias = L->bias; cp.Cout = s.cout;
       cp.y = o.p; cp.out_dt = DT_F32; cp.Hout = Ho; cp.Wout = Wo; cp.ldo = s.cout; cp.choff = 0;
       cp.osy = cp.osx = 1; cp.epi = EPI_LINEAR; cp.scale = 1.0f;
-      CK(direct_launch(cp, cw.CoutP, precision == SE_PREC_FP32_EXACT, st));
-      CK(nhwc_to_nchw(o.p, DT_F32, y, B, s.cout, Ho * Wo, s.cout, 0, st));
+      CK(direct_launch(cp, cw.CoutP, precision == SE_PREC_FP32_EXACT, c.stream));
+      CK(nhwc_to_nchw(o.p, DT_F32, y, B, s.cout, Ho * Wo, s.cout, 0, c.stream));
       c.put(o);
     } else {
       const int cg = s.cout / 2;
@@ -1522,16 +1535,16 @@ int se_gated_conv_forward(se_model* m, char net, const char* layer, const float*
       if (c.split()) {
         const int cbo = (cg + 7) / 8;
         Buf o = c.get(act_bytes(c, Ho, Wo, cg, 1));
-        if (cg % 8) CK(fill_zero(o.p, o.bytes, st));
+        if (cg % 8) CK(fill_zero(o.p, o.bytes, c.stream));
         int r = run_layer(c, *L, vin, o.p, 2 * cbo, 0, 1);
         if (r) return r;
-        CK(split_to_f32(o.p, y, B, cg, Ho * Wo, cbo, 0, 0, st));
+        CK(split_to_f32(o.p, y, B, cg, Ho * Wo, cbo, 0, 0, c.stream));
         c.put(o);
       } else {
         Buf o = c.get((size_t)B * Ho * Wo * cg * c.esz());
         int r = run_layer(c, *L, vin, o.p, cg, 0, 0);
         if (r) return r;
-        CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, st));
+        CK(nhwc_to_nchw(o.p, dt, y, B, cg, Ho * Wo, cg, 0, c.stream));
         c.put(o);
       }
     }
@@ -1555,20 +1568,20 @@ int se_contextual_attention_forward(const float* feat, const float* mask_s, int 
     Buf o = c.get((size_t)B * h * w * C * c.esz());
     if (precision == SE_PREC_BF16_TC && C == 96 && h % 2 == 0 && w % 2 == 0) {
       // the layouts netG uses on the tensor-core path: space-to-depth channel-blocked in, channel-blocked out
-      CK(nchw_to_c8_s2d(feat, in.p, B, C, h, w, st));
+      CK(nchw_to_c8_s2d(feat, in.p, B, C, h, w, c.stream));
       View fv = c8view(in.p, h, w, C, 4 * (C / 8), 0);
       fv.c8 = 2;
       int r = run_cam_tc(c, fv, mask_s, o.p, attn);
       if (r) return r;
-      CK(c8_to_nchw(o.p, out, B, C, h * w, st));
+      CK(c8_to_nchw(o.p, out, B, C, h * w, c.stream));
       c.put(o);
       c.put(in);
       return 0;
     }
-    CK(nchw_to_nhwc(feat, in.p, dt, B, C, h * w, C, 0, st));
+    CK(nchw_to_nhwc(feat, in.p, dt, B, C, h * w, C, 0, c.stream));
     int r = run_cam(c, nhwc(in.p, h, w, C, C), mask_s, o.p, C, attn);
     if (r) return r;
-    CK(nhwc_to_nchw(o.p, dt, out, B, C, h * w, C, 0, st));
+    CK(nhwc_to_nchw(o.p, dt, out, B, C, h * w, C, 0, c.stream));
     c.put(o);
     c.put(in);
     return 0;

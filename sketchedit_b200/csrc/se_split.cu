@@ -1,5 +1,5 @@
 // Glue kernels of the fp32-on-tensor-cores mode (SE_PREC_FP32_TC): activations are stored "split half" (DT_F16X2, se_common.cuh):
-// value = hi + lo with hi = fp16(v), lo = fp16(v - hi), in channel-blocked tensors whose lo blocks follow the hi blocks
+// value * 64 (kSplitActScale, se_common.cuh) = hi + lo with hi = fp16(64 v), lo = fp16(64 v - hi), in channel-blocked tensors whose lo blocks follow the hi blocks
 // ([N][2*CB][H][W][8]; space-to-depth: [N][4 parities][2][CB][H/2][W/2][8]). Everything here is the split-half twin of a
 // kernel in se_misc.cu: input packing, heads, global pooling, layout conversion (reference call sites are cited there).
 #include <cuda_fp16.h>
@@ -15,8 +15,9 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo
   uint32_t h[4], l[4];
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
-    const __half h0 = __float2half_rn(v[k]), h1 = __float2half_rn(v[k + 1]);
-    const __half l0 = __float2half_rn(v[k] - __half2float(h0)), l1 = __float2half_rn(v[k + 1] - __half2float(h1));
+    const float s0 = fminf(fmaxf(v[k] * kSplitActScale, -kSplitActMax), kSplitActMax), s1 = fminf(fmaxf(v[k + 1] * kSplitActScale, -kSplitActMax), kSplitActMax);
+    const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+    const __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
     h[k >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
     l[k >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
   }
@@ -29,8 +30,8 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float2 a = __half22float2(h[k]), b = __half22float2(l[k]);
-    v[2 * k] = a.x + b.x;
-    v[2 * k + 1] = a.y + b.y;
+    v[2 * k] = (a.x + b.x) * kSplitActInv;
+    v[2 * k + 1] = (a.y + b.y) * kSplitActInv;
   }
 }
 
@@ -235,7 +236,7 @@ __global__ void nchw_to_split_kernel(const float* __restrict__ x, __half* __rest
   r /= H;
   const int c = (int)(r % C);
   const long long b = r / C;
-  const float v = x[i];
+  const float v = fminf(fmaxf(x[i] * kSplitActScale, -kSplitActMax), kSplitActMax);
   const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
   const int CB = (C + 7) / 8;
   size_t oh, ol;
@@ -270,7 +271,7 @@ __global__ void split_to_f32_kernel(const __half* __restrict__ x, float* __restr
   else { p = i % HW; c = (int)((i / HW) % C); b = i / ((long long)C * HW); }
   const int cc = choff + c;
   const size_t oh = (((size_t)b * 2 * ld + (cc >> 3)) * HW + p) * 8 + (cc & 7);
-  y[i] = __half2float(x[oh]) + __half2float(x[oh + (size_t)ld * HW * 8]);
+  y[i] = (__half2float(x[oh]) + __half2float(x[oh + (size_t)ld * HW * 8])) * kSplitActInv;
 }
 int split_to_f32(const void* x, float* y, int B, int C, int HW, int ld, int choff, int nhwc, cudaStream_t s) {
   const long long total = (long long)B * C * HW;
@@ -284,7 +285,7 @@ __global__ void nhwc_f32_to_split_kernel(const float* __restrict__ x, __half* __
   if (i >= total) return;
   const int c = (int)(i % C);
   const long long p = (i / C) % HW, b = i / ((long long)C * HW);
-  const float v = x[i];
+  const float v = fminf(fmaxf(x[i] * kSplitActScale, -kSplitActMax), kSplitActMax);
   const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
   const int cc = choff + c;
   const size_t oh = (((size_t)b * 2 * ld + (cc >> 3)) * HW + p) * 8 + (cc & 7);

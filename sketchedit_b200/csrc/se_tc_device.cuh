@@ -447,20 +447,28 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
 }
 
 // Split-half mode (DT_F16X2, the fp32-on-tensor-cores path): same gate, fp32-accurate math (ex2 / rcp approximations are good
-// to ~2^-22; no tanh.approx), each output stored as hi = fp16(v) and lo = fp16(v - hi), the lo block split_stride further on.
+// to ~2^-22; no tanh.approx), each output v stored as hi = fp16(64 v) and lo = fp16(64 v - hi), the lo block split_stride further on.
 // The accumulator column of a gate still holds 0.5 * g (weights are packed pre-multiplied by 0.5, exact), hb = 0.5 * b'.
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// `s` = 1 / (activation scale * weight scale) of the split-half operands (se_common.cuh: kSplitActScale, ClassW::s_wscale).
+// ELU's exp(x) - 1 cancels near 0 (ex2.approx is good to 2^-22 of exp(x), i.e. 2.4e-7 ABSOLUTE, 2.4e-4 of x = -1e-3):
+// above -1/16 the degree-5 Taylor polynomial of expm1 is used instead (remainder < 1e-10).
 template <bool kElu>
-__device__ __forceinline__ float gate_one_exact(float f, float ghalf, float b, float hb) {
-  const float fv = f + b;
+__device__ __forceinline__ float gate_one_exact(float f, float ghalf, float b, float hb, float s) {
+  const float fv = fmaf(f, s, b);
   float a;
-  if (kElu) a = fv > 0.0f ? fv : (ex2_approx(fv * 1.4426950408889634f) - 1.0f);
-  else a = fmaxf(fv, 0.0f);
-  const float gx = 2.0f * (ghalf + hb);
+  if (kElu) {
+    const float big = ex2_approx(fv * 1.4426950408889634f) - 1.0f;
+    const float small = fv * fmaf(fv, fmaf(fv, fmaf(fv, fmaf(fv, 1.0f / 120.0f, 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
+    a = fv > 0.0f ? fv : (fv > -0.0625f ? small : big);
+  } else {
+    a = fmaxf(fv, 0.0f);
+  }
+  const float gx = 2.0f * fmaf(ghalf, s, hb);
   return a * rcp_approx(1.0f + ex2_approx(-gx * 1.4426950408889634f));
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -492,8 +500,10 @@ __device__ __forceinline__ void tc_epilogue_gated_split(const EpiParams& e, cons
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {
-        const float v0 = gate_one_exact<kElu>(f[k], g[k], cst[c0 + k], cst[2 * cst_n + goff + c0 + k]);
-        const float v1 = gate_one_exact<kElu>(f[k + 1], g[k + 1], cst[c0 + k + 1], cst[2 * cst_n + goff + c0 + k + 1]);
+        float v0 = gate_one_exact<kElu>(f[k], g[k], cst[c0 + k], cst[2 * cst_n + goff + c0 + k], e.scale);
+        float v1 = gate_one_exact<kElu>(f[k + 1], g[k + 1], cst[c0 + k + 1], cst[2 * cst_n + goff + c0 + k + 1], e.scale);
+        v0 = fminf(fmaxf(v0 * kSplitActScale, -kSplitActMax), kSplitActMax);
+        v1 = fminf(fmaxf(v1 * kSplitActScale, -kSplitActMax), kSplitActMax);
         const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
         hi[k >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
         lo[k >> 1] = pack_f16x2(v0 - __half2float(h0), v1 - __half2float(h1));

@@ -11,6 +11,7 @@
 #   full:REGEX[:ARGS]   ncu --set full --import-source on of kernels matching REGEX (-c 3) -> gpurun_out/full_<..>.ncu-rep
 #   all[:ARGS]          light ncu capture (speed-of-light, memory, tensor pipe, DRAM bytes) of EVERY launch of one forward
 #                                                                    -> gpurun_out/all_<ARGS>.ncu-rep (tools/ncu_summary.py)
+#   precision[:B,H,W]  tools/precision_report.py: error of every precision mode vs the oracle -> gpurun_out/precision.md
 #   probe[:CASES]       SE_TC_DEBUG role timers of single layers (tools/tc_probe.py)
 #   env:K=V / unset:K   export K=V / unset K for the following steps
 #
@@ -56,6 +57,9 @@ for step in "$@"; do
         --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
         --clock-control none -s ${SKIP:-170} -c ${COUNT:-90} -o gpurun_out/$t -f python bench.py --steps 1 --warmup 3 --no-latency $args > gpurun_out/$t.log 2>&1
       ls -la gpurun_out/$t.ncu-rep ;;
+    precision)
+      a=$(echo "$rest" | tr ',' ' ')
+      timeout 900 python tools/precision_report.py $a > gpurun_out/precision.md 2> gpurun_out/precision.err; cat gpurun_out/precision.md; tail -3 gpurun_out/precision.err ;;
     probe)
       ( SE_TC_DEBUG=1 SE_PROBE_CASES=$rest PB=${PB:-32} timeout 300 python tools/tc_probe.py 2>&1 | grep -E "^==|^\[tc\]|^\[c8\]" ) > gpurun_out/probe.log 2>&1
       awk '/^==/{n=$0; c=0} /^\[(tc|c8)\]/{c++; if(c==1) print n "  " $0}' gpurun_out/probe.log | cut -c1-360 | awk '!seen[$0]++' ;;
