@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsketchedit_b200.so")
+LIB_PATH = os.environ.get("SE_B200_LIB") or os.path.join(_HERE, "libsketchedit_b200.so")   # SE_B200_LIB: an A/B build of the same sources
 
 _c_void_p = ctypes.c_void_p
 _c_int = ctypes.c_int

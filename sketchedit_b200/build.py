@@ -40,7 +40,7 @@ def build(force=False, verbose=True):
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("SE_NVCC_EXTRA", "").split()   # A/B builds (-DSE_...)
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
@@ -54,11 +54,12 @@ def build(force=False, verbose=True):
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    out_lib = os.environ.get("SE_LIB_OUT", LIB)   # A/B builds go next to the product library, selected with SE_B200_LIB at load time
+    cmd = [nvcc, "-shared", "-o", out_lib] + objs + ["-lcudart"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return LIB
+    return out_lib
 
 
 if __name__ == "__main__":

@@ -654,7 +654,6 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     if (split) {
       SE_REQUIRE(cw.has_split && in.c8 && out_c8, "split-half mode runs on channel-blocked activations (layer " + L.name + ")");
       cp.f16x2 = 1;
-      cp.scale = 1.0f / (kSplitActScale * cw.s_wscale);   // accumulator -> true pre-activation (exact: powers of two)
       // hi blocks first, lo blocks after them: per image (channel-blocked) or per parity group (space-to-depth)
       cp.out_split_stride = out_c8 == 2 ? (long long)(ldo / 8) * (Ho * cw.osy / 2) * (Wo * cw.osx / 2) : (long long)(ldo / 2) * (Ho * cw.osy) * (Wo * cw.osx);
     }
@@ -677,7 +676,8 @@ static int run_layer(Ctx& c, Layer& L, const View& in, void* out, int ldo, int c
     cp.Hout = Ho * cw.osy; cp.Wout = Wo * cw.osx; cp.ldo = ldo; cp.choff = choff;
     cp.osy = cw.osy; cp.ooy = cw.ooy; cp.osx = cw.osx; cp.oox = cw.oox;
     cp.epi = s.act == 1 ? EPI_GATE_RELU : EPI_GATE_ELU;
-    cp.scale = 1.0f; cp.colscale = nullptr;
+    cp.scale = split ? 1.0f / (kSplitActScale * cw.s_wscale) : 1.0f;   // split-half: accumulator -> true pre-activation (exact: powers of two)
+    cp.colscale = nullptr;
     if (L.fused_pair) {
       // two space-to-depth tensors of 4 x 3 blocks each, back to back per image (ldo = 24 blocks): blocks 3..5 of the fused
       // output are blocks 0..2 of the second one, 12 - 3 = 9 block planes further on
@@ -1140,6 +1140,7 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
 
 // run `fn` twice: dry (arena peak) then for real
 static const bool g_graphs_on = getenv("SE_NO_GRAPHS") == nullptr;
+static const bool g_graph_log = getenv("SE_GRAPH_LOG") != nullptr;   // one stderr line per capture / failed capture
 constexpr size_t kMaxGraphs = 16;
 
 template <typename F>
@@ -1240,9 +1241,11 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
         se_model::GraphEntry e;
         e.key = key; e.exec = exec; e.arena = m->arena; e.launches = g_launches; e.tick = ++m->tick;
         m->graphs.push_back(e);
+        if (g_graph_log) fprintf(stderr, "[graph] captured B=%d prec=%d launches=%d (%zu cached)\n", B, prec, e.launches, m->graphs.size());
         SE_CUDA_OK(cudaGraphLaunch(exec, gs));
         return bridge_out();
       }
+      if (g_graph_log) fprintf(stderr, "[graph] capture failed: rc=%d end=%s exec=%p\n", rc, cudaGetErrorString(ce), (void*)exec);
       if (graph) cudaGraphDestroy(graph);
       (void)cudaGetLastError();
       m->seen[key] = -1000000;   // not capturable: stay eager for this signature
@@ -1250,12 +1253,14 @@ static int with_arena(se_model* m, int prec, int B, cudaStream_t stream, F fn, s
       c.arena.reset((char*)m->arena);
       g_launches = 0;
     } else {
+      if (g_graph_log) fprintf(stderr, "[graph] cudaStreamBeginCapture failed: %s\n", cudaGetErrorString(cudaPeekAtLastError()));
       (void)cudaGetLastError();  // a failed cudaStreamBeginCapture leaves a sticky error behind
       m->seen[key] = -1000000;
     }
     rb = bridge_out();           // (orders nothing new, but keeps the two streams' event pairs balanced)
     if (rb) return rb;
   }
+  if (g_graph_log && graphable) fprintf(stderr, "[graph] eager run B=%d prec=%d (sighting %d of this signature, %zu signatures seen)\n", B, prec, m->seen[key], m->seen.size());
   return fn(c);
 }
 

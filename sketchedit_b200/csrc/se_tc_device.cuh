@@ -23,18 +23,38 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // ONE asm block on purpose: written as a C++ loop (per-lane `done` flag, early return, printf on timeout) ptxas treated
 // everything after a wait as possibly divergent, kept every later value in vector registers and fed each tcgen05.mma operand
 // through R2UR moves (4-7 per MMA; the stems' tensor pipe was 35 % active). (`tag` names the wait site; kept for debugging builds.)
+#ifndef SE_WAIT_VARIANT
+#define SE_WAIT_VARIANT 0
+#endif
+#if SE_WAIT_VARIANT == 1      // read the timer after every failed attempt
+#define SE_WAIT_HINT ""
+#define SE_WAIT_SPINS "1"
+#elif SE_WAIT_VARIANT == 2    // let the hardware suspend the thread for up to ~2 us per attempt
+#define SE_WAIT_HINT ", 2000"
+#define SE_WAIT_SPINS "256"
+#else
+#define SE_WAIT_HINT ""
+#define SE_WAIT_SPINS "256"
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   (void)tag;
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 t0, t1;\n\t"
-      "mov.u64 t0, %%globaltimer;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "{\n\t.reg .pred p;\n\t.reg .b64 t0, t1;\n\t.reg .b32 n;\n\t"
+      "mov.u64 t0, 0;\n\t"
+      "OUTER_%=:\n\t"
+      "mov.u32 n, 0;\n\t"
+      "INNER_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1" SE_WAIT_HINT ";\n\t"
       "@p bra DONE_%=;\n\t"
-      "mov.u64 t1, %%globaltimer;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, " SE_WAIT_SPINS ";\n\t"
+      "@p bra INNER_%=;\n\t"
+      "mov.u64 t1, %%globaltimer;\n\t"      // only after 256 failed attempts: the timer read is slow and must stay off the wake-up path
+      "setp.eq.u64 p, t0, 0;\n\t"
+      "@p mov.u64 t0, t1;\n\t"
       "sub.u64 t1, t1, t0;\n\t"
       "setp.lt.u64 p, t1, 2000000000;\n\t"
-      "@p bra WAIT_%=;\n\t"
+      "@p bra OUTER_%=;\n\t"
       "trap;\n\t"
       "DONE_%=:\n\t}"
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -44,15 +64,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
   (void)tag;
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 t0, t1;\n\t"
-      "mov.u64 t0, %%globaltimer;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "{\n\t.reg .pred p;\n\t.reg .b64 t0, t1;\n\t.reg .b32 n;\n\t"
+      "mov.u64 t0, 0;\n\t"
+      "OUTER_%=:\n\t"
+      "mov.u32 n, 0;\n\t"
+      "INNER_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1" SE_WAIT_HINT ";\n\t"
       "@p bra DONE_%=;\n\t"
-      "mov.u64 t1, %%globaltimer;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, " SE_WAIT_SPINS ";\n\t"
+      "@p bra INNER_%=;\n\t"
+      "mov.u64 t1, %%globaltimer;\n\t"      // only after 256 failed attempts: the timer read is slow and must stay off the wake-up path
+      "setp.eq.u64 p, t0, 0;\n\t"
+      "@p mov.u64 t0, t1;\n\t"
       "sub.u64 t1, t1, t0;\n\t"
       "setp.lt.u64 p, t1, 2000000000;\n\t"
-      "@p bra WAIT_%=;\n\t"
+      "@p bra OUTER_%=;\n\t"
       "trap;\n\t"
       "DONE_%=:\n\t}"
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -384,6 +411,7 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
   auto boff = [&](int b) -> uint32_t { return obase + (uint32_t)b * ostep + (b >= e.blk_split ? (uint32_t)e.blk_jump : 0u); };
   // 4 outputs [c, c+4) from f[k..k+3], g[k..k+3]
   auto gate4 = [&](float* f, const float* g, int c, int k) {
+    if (e.dbg == 1) { f[k] += g[k]; f[k + 1] += g[k + 1]; f[k + 2] += g[k + 2]; f[k + 3] += g[k + 3]; return; }
     const float4 b = lds128(cs0 + c * 4), bl = lds128(cs0 + (cst_n + c) * 4), hb = lds128(cs0 + (2 * cst_n + goff + c) * 4);
     f[k] = gate_one<kElu>(f[k], g[k], b.x, bl.x, hb.x);
     f[k + 1] = gate_one<kElu>(f[k + 1], g[k + 1], b.y, bl.y, hb.y);
@@ -393,12 +421,18 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
   auto do16 = [&](int b) {
     const int c0 = b * 8;
     float f[16], g[16];
+    if (e.dbg == 3) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { f[k] = (float)ox; g[k] = (float)oy; }
+    } else {
     tmem_ld16(taddr + c0, f);
     tmem_ld16(taddr + goff + c0, g);
+    }
     tmem_ld_wait();
     if (valid) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) gate4(f, g, c0 + 4 * q, 4 * q);
+      if (e.dbg == 2) return;
       ybase[boff(b)] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
       ybase[boff(b + 1)] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
     }
@@ -543,6 +577,11 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
     float f[PASS][8], g[PASS][8];
 #pragma unroll
     for (int j = 0; j < PASS; ++j) {
+      if (e.dbg == 3) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { f[j][k] = (float)ox; g[j][k] = (float)oy; }
+        continue;
+      }
       tmem_ld8(taddr + (b0 + j) * 8, f[j]);
       tmem_ld8(taddr + goff + (b0 + j) * 8, g[j]);
     }
@@ -553,8 +592,11 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int c = (b0 + j) * 8 + k;                // compile time
+          if (e.dbg == 1) f[j][k] = f[j][k] + g[j][k];
+          else
           f[j][k] = gate_one<kElu, true>(f[j][k], g[j][k], cst[0][c], 0.0f, cst[2][c]);   // both constants: immediate constant-bank operands
         }
+        if (e.dbg != 2)
         ybase[obase + (uint32_t)(b0 + j) * ostep] =
             make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]), pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
       }

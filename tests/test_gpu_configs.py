@@ -190,12 +190,16 @@ def test_test_py_end_to_end(prec, tmp_path):
         got = cv2.imread(str(odir / (n + ".png")), cv2.IMREAD_COLOR)          # BGR, HWC
         got_m = cv2.imread(str(omdir / (n + ".png")), cv2.IMREAD_GRAYSCALE)
         image, sketch = tensors[n]
-        comp, mask, _ = eng.inference(image.cuda(), sketch.cuda(), precision=prec)
+        comp, mask, ex = eng.inference(image.cuda(), sketch.cuda(), precision=prec, want=("mask_bin",))
         g, m = O.to_uint8_outputs(comp.cpu(), mask.cpu())
         assert np.array_equal(got, g[0].transpose(1, 2, 0)[..., ::-1]), n
         assert np.array_equal(got_m, m[0]), n
         if prec == "fp32":
             ref = O.inference(WM, WG, image, sketch)
+            flipped = ex["mask_bin"].cpu() != ref["mask_bin"]
+            if bool(flipped.any()):   # a soft-mask value within fp32 noise of the 0.5 threshold (see _check_batch): compare netG on OUR mask
+                assert int(flipped.sum()) <= 2 and float((ref["mask"] - 0.5).abs()[flipped].max()) <= 5e-5
+                ref = O.inference(WM, WG, image, sketch, mask_bin_override=ex["mask_bin"].cpu())
             rg, rm = O.to_uint8_outputs(ref["composed"], ref["mask"])
             d = np.abs(got.astype(int) - rg[0].transpose(1, 2, 0)[..., ::-1].astype(int))
             assert d.max() <= 1 and (d != 0).mean() <= 2e-3, (d.max(), (d != 0).mean())   # truncation ties: |err| ~1e-5 of 1/127.5 per level

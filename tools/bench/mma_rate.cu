@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(384, 1) mma_rate(int N, int reps, int mode, in
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t sA = base, sB = base + 65536;
     uint32_t a_hi, a_lo0, b_hi;
-    if (mode == 0) { a_hi = (1024u >> 4) | (1u << 14) | (2u << 29); a_lo0 = 0; b_hi = a_hi; }
+    if (mode == 0 || mode == 3) { a_hi = (1024u >> 4) | (1u << 14) | (2u << 29); a_lo0 = 0; b_hi = a_hi; }
     else if (mode == 1) { a_hi = ((uint32_t)(sbo >> 4) & 0x3FFF) | (1u << 14); a_lo0 = (((uint32_t)lbo >> 4) & 0x3FFF) << 16; b_hi = (1024u >> 4) | (1u << 14) | (2u << 29); }
     else { a_hi = (512u >> 4) | (1u << 14) | (4u << 29); a_lo0 = 0; b_hi = a_hi; }
     const uint32_t lead = elect_one() ? 1u : 0u;
@@ -77,6 +77,19 @@ __global__ void __launch_bounds__(384, 1) mma_rate(int N, int reps, int mode, in
       goto finish;
     }
     const long long t0 = clock64();
+    if (mode == 3) {
+      // accumulator alternation: consecutive MMAs go to `sbo` different accumulators (128 columns apart), switching every `lbo` MMAs
+      // (lbo = log2 of the burst length, sbo = number of accumulators, a power of two: shifts and masks only)
+      const int bsh = lbo, amask = sbo - 1;
+      for (int r = 0; r < reps; ++r) {
+        const uint32_t a0 = (sA >> 4) + (r & 7) * 8, b0 = (sB >> 4) + (r & 7) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = r * 4 + k;
+          umma_bf16_if32(lead, tmem + (uint32_t)((((i >> bsh) & amask)) << 7), a_lo0 | (a0 + 2 * k), a_hi, b0 + 2 * k, b_hi, idesc, r >= 16 ? 1u : 0u);
+        }
+      }
+    } else
     for (int r = 0; r < reps; ++r) {
       const uint32_t a0 = (sA >> 4) + (r & 7) * 8, b0 = (sB >> 4) + (r & 7) * 8;
 #pragma unroll
@@ -124,6 +137,18 @@ int main() {
       printf("concurrent tcgen05.ld.x%-2d by 8 warps  N=%3d  MMA %.1f cyc (ideal %d)   loads per warp during run: %llu  (= 1 per %.0f cyc)\n", ld, N,
              (double)h[1] / (reps * 4), N / 2 > 40 ? N / 2 : 40, h[2], h[2] ? (double)h[1] / h[2] : 0.0);
     }
+  for (int N : {32, 48, 96})
+    for (int nacc : {1, 2, 4})
+      for (int bsh : {0, 1, 3, 4}) {
+        const int burst = 1 << bsh;
+        if (nacc == 1 && burst > 1) continue;
+        mma_rate<<<148, 128, 160 * 1024>>>(N, reps, 3, bsh, nacc, 0, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("acc test: %s\n", cudaGetErrorString(e)); return 1; }
+        unsigned long long h[2];
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("accumulators=%d switch every %2d MMAs  N=%3d  issue %.1f cyc/MMA  complete %.1f cyc/MMA\n", nacc, burst, N, (double)h[0] / (reps * 4), (double)h[1] / (reps * 4));
+      }
   struct Case { int mode, lbo, sbo; const char* name; } cases[] = {
       {0, 0, 0, "A SW128 / B SW128"}, {2, 0, 0, "A SW64 / B SW64"}, {1, 2880, 160, "A no-swizzle LBO=2880 SBO=160 (halo 18x10)"},
       {1, 2048, 128, "A no-swizzle LBO=2048 SBO=128 (per-tap 16x8)"}, {1, 16, 208, "A no-swizzle LBO=16 SBO=208 (stem)"},
