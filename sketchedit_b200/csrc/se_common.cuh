@@ -109,7 +109,6 @@ struct EpiParams {
   // space-to-depth output (ldo / 4 unless two such tensors share the buffer). blk_split = 1 << 20: off.
   int blk_split, blk_jump, par_stride;
   int nsplit, split_stride;   // nsplit = 2: split-half output (DT_F16X2): the lo part of every block is stored split_stride (16 B units) further on
-  int dbg;        // EXPERIMENT (SE_EPI_DBG): 1 no gate math, 2 no stores, 3 no TMEM loads
   int has_bias;   // 0: the launch has no bias vector (attention GEMMs): no per-column constants are staged in shared memory
   int goff;   // gated epilogues: accumulator column of gate channel 0 (= Cout/2 rounded up to 8; the weight image
               // places feature c at column c and its gate at goff + c, columns in between are zero weights)

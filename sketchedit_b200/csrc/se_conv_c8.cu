@@ -473,7 +473,6 @@ void fill_epi(const ConvParams& c, int NT, EpiParams* e) {
   e->epi = c.epi; e->scale = c.scale; e->colscale = c.colscale;
   e->Cout = c.Cout; e->NT = NT;
   e->has_bias = c.bias != nullptr ? 1 : 0;
-  { static const int dbg = getenv("SE_EPI_DBG") ? atoi(getenv("SE_EPI_DBG")) : 0; e->dbg = dbg; }
   e->blk_split = c.out_blk_split > 0 ? c.out_blk_split : (1 << 20);
   e->blk_jump = c.out_blk_split > 0 ? c.out_blk_jump : 0;
   e->par_stride = c.out_par_stride > 0 ? c.out_par_stride : (c.ldo >> 2);

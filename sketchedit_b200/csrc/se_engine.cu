@@ -20,6 +20,7 @@
 #include "se_conv_direct.h"
 #include "se_conv_c8.h"
 #include "se_cam.h"
+#include "se_gemm_split.h"
 #include "se_conv_tc.h"
 #include "se_misc.h"
 
@@ -919,6 +920,28 @@ static int run_cam(Ctx& c, const View& f, const float* mask_s, void* out, int ou
   return 0;
 }
 
+// Attention of the fp32-on-tensor-cores mode: f fp32 NHWC [B][h][w][96] -> out fp32 NHWC, split-half fp16 tcgen05 GEMMs (se_gemm_split.cu)
+static int run_cam_split(Ctx& c, const float* f, int h, int w, int C, const float* mask_s, float* out) {
+  CamSplitPlan pl;
+  {
+    int rc = cam_split_plan(c.B, h, w, C, &pl);
+    if (rc) return rc;
+  }
+  Buf rnorm = c.get((size_t)c.B * C * 4), colm = c.get((size_t)c.B * pl.L * 4);
+  Buf q = c.get(pl.q_bytes), kn = c.get(pl.q_bytes), sb = c.get(pl.s_bytes), pb = c.get(pl.p_bytes), ob = c.get(pl.o_bytes);
+  c.tag("plane_sumsq/rnorm|attention key norm", 0, 0, 0, (double)c.B * h * w * C * 4);
+  CK(plane_reduce(f, DT_F32, c.B, h * w, C, C, 0, RED_RNORM, (float*)rnorm.p, c.stream));
+  c.tag("cam_colmask_kernel", 0, 0, 0, (double)c.B * h * w * 4);
+  CK(cam_colmask(mask_s, (float*)colm.p, c.B, h, w, pl.hs, pl.ws, 0.1f, c.stream));
+  const double fl = 2.0 * c.B * (double)pl.L * pl.L * pl.KQ * 2.0;   // S and PV, algorithmic (one product each)
+  c.tag("gemm_split_kernel x2 (split-half fp16 x3) + pack / softmax / fold|contextual attention", 1, fl, 3.0 * 2.0 * c.B * (double)pl.Mp * pl.Mp * pl.KQ * 2.0,
+        (double)c.B * h * w * C * 4 * 2 + 2.0 * pl.q_bytes * 2 + 2.0 * pl.s_bytes + 2.0 * pl.p_bytes + 2.0 * pl.o_bytes);
+  CK(cam_forward_split(f, (const float*)rnorm.p, (const float*)colm.p, out, pl, q.p, kn.p, (float*)sb.p, pb.p, (float*)ob.p, c.stream));
+  if (!c.dry) g_launches += 4;   // pack, S GEMM, softmax, PV GEMM, fold behind one call
+  c.put(ob); c.put(pb); c.put(sb); c.put(kn); c.put(q); c.put(colm); c.put(rnorm);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ networks
 static const std::initializer_list<const char*> kTrunk9 = {"conv1", "conv2_downsample", "conv3", "conv4_downsample", "conv5",
                                                            "conv6", "conv7_atrous", "conv8_atrous", "conv9_atrous"};
@@ -1099,13 +1122,18 @@ static int run_netG(Ctx& c, const float* x, const float* x2, const float* mask, 
       CK(avgpool4(mask, (float*)ms.p, c.B, H, W, c.stream));
       Buf camo = c.get((size_t)c.B * h * w * 96 * e);
       if (c.split()) {
-        // split-half mode: the attention itself runs on the fp32 CUDA-core kernels (exact class) between two layout conversions
+        // split-half mode: fp32 NHWC in / out of the attention (split-half fp16 GEMMs over explicit patch matrices, se_gemm_split.cu)
         Buf f32 = c.get((size_t)c.B * h * w * 96 * 4), o32 = c.get((size_t)c.B * h * w * 96 * 4);
         CK(split_to_f32(pm.p, (float*)f32.p, c.B, 96, h * w, pm.ld / 2, 0, 1, c.stream));
-        const int saved = c.prec;
-        c.prec = SE_PREC_FP32_EXACT;
-        rc = run_cam(c, nhwc(f32.p, h, w, 96, 96), (const float*)ms.p, o32.p, 96, nullptr, 0);
-        c.prec = saved;
+        static const bool cuda_core_cam = getenv("SE_SPLIT_CAM_DIRECT") != nullptr;   // A/B: the fp32 CUDA-core attention instead
+        if (cuda_core_cam) {
+          const int saved = c.prec;
+          c.prec = SE_PREC_FP32_EXACT;
+          rc = run_cam(c, nhwc(f32.p, h, w, 96, 96), (const float*)ms.p, o32.p, 96, nullptr, 0);
+          c.prec = saved;
+        } else {
+          rc = run_cam_split(c, (const float*)f32.p, h, w, 96, (const float*)ms.p, (float*)o32.p);
+        }
         if (rc) return rc;
         CK(nhwc_f32_to_split((const float*)o32.p, camo.p, c.B, 96, h * w, 12, 0, c.stream));
         c.put(o32); c.put(f32);
@@ -1565,10 +1593,23 @@ int se_contextual_attention_forward(const float* feat, const float* mask_s, int 
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   if (!holder) { holder = new se_model(); holder->finalized = true; }
-  if (precision == SE_PREC_FP32_TC) precision = SE_PREC_FP32_EXACT;   // the attention of the fp32 modes runs on the fp32 CUDA-core kernels
+  // fp32-on-tensor-cores mode: split-half GEMM attention (needs 16 * C to be a multiple of 256 and no attention-map output);
+  // everything else of the fp32 modes runs on the fp32 CUDA-core kernels
+  const bool split_cam = precision == SE_PREC_FP32_TC && C % 16 == 0 && attn == nullptr && h % 2 == 0 && w % 2 == 0 && getenv("SE_SPLIT_CAM_DIRECT") == nullptr;
+  if (precision == SE_PREC_FP32_TC) precision = SE_PREC_FP32_EXACT;
   cudaStream_t st = (cudaStream_t)stream;
   return with_arena(holder, precision, B, st, [&](Ctx& c) -> int {
     const int dt = c.act_dt();
+    if (split_cam) {
+      Buf in = c.get((size_t)B * h * w * C * 4), o = c.get((size_t)B * h * w * C * 4);
+      CK(nchw_to_nhwc(feat, in.p, DT_F32, B, C, h * w, C, 0, c.stream));
+      int r = run_cam_split(c, (const float*)in.p, h, w, C, mask_s, (float*)o.p);
+      if (r) return r;
+      CK(nhwc_to_nchw(o.p, DT_F32, out, B, C, h * w, C, 0, c.stream));
+      c.put(o);
+      c.put(in);
+      return 0;
+    }
     Buf in = c.get((size_t)B * h * w * C * c.esz());
     Buf o = c.get((size_t)B * h * w * C * c.esz());
     if (precision == SE_PREC_BF16_TC && C == 96 && h % 2 == 0 && w % 2 == 0) {

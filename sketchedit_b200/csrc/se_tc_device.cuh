@@ -411,7 +411,6 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
   auto boff = [&](int b) -> uint32_t { return obase + (uint32_t)b * ostep + (b >= e.blk_split ? (uint32_t)e.blk_jump : 0u); };
   // 4 outputs [c, c+4) from f[k..k+3], g[k..k+3]
   auto gate4 = [&](float* f, const float* g, int c, int k) {
-    if (e.dbg == 1) { f[k] += g[k]; f[k + 1] += g[k + 1]; f[k + 2] += g[k + 2]; f[k + 3] += g[k + 3]; return; }
     const float4 b = lds128(cs0 + c * 4), bl = lds128(cs0 + (cst_n + c) * 4), hb = lds128(cs0 + (2 * cst_n + goff + c) * 4);
     f[k] = gate_one<kElu>(f[k], g[k], b.x, bl.x, hb.x);
     f[k + 1] = gate_one<kElu>(f[k + 1], g[k + 1], b.y, bl.y, hb.y);
@@ -421,18 +420,12 @@ __device__ __forceinline__ void tc_epilogue_gated_fast(const EpiParams& e, const
   auto do16 = [&](int b) {
     const int c0 = b * 8;
     float f[16], g[16];
-    if (e.dbg == 3) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) { f[k] = (float)ox; g[k] = (float)oy; }
-    } else {
     tmem_ld16(taddr + c0, f);
     tmem_ld16(taddr + goff + c0, g);
-    }
     tmem_ld_wait();
     if (valid) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) gate4(f, g, c0 + 4 * q, 4 * q);
-      if (e.dbg == 2) return;
       ybase[boff(b)] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
       ybase[boff(b + 1)] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
     }
@@ -577,11 +570,6 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
     float f[PASS][8], g[PASS][8];
 #pragma unroll
     for (int j = 0; j < PASS; ++j) {
-      if (e.dbg == 3) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { f[j][k] = (float)ox; g[j][k] = (float)oy; }
-        continue;
-      }
       tmem_ld8(taddr + (b0 + j) * 8, f[j]);
       tmem_ld8(taddr + goff + (b0 + j) * 8, g[j]);
     }
@@ -592,11 +580,8 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int c = (b0 + j) * 8 + k;                // compile time
-          if (e.dbg == 1) f[j][k] = f[j][k] + g[j][k];
-          else
           f[j][k] = gate_one<kElu, true>(f[j][k], g[j][k], cst[0][c], 0.0f, cst[2][c]);   // both constants: immediate constant-bank operands
         }
-        if (e.dbg != 2)
         ybase[obase + (uint32_t)(b0 + j) * ostep] =
             make_uint4(pack_bf16x2(f[j][0], f[j][1]), pack_bf16x2(f[j][2], f[j][3]), pack_bf16x2(f[j][4], f[j][5]), pack_bf16x2(f[j][6], f[j][7]));
       }

@@ -87,6 +87,20 @@ def test_contextual_attention_fp32(h, w, B):
 
 
 @pytest.mark.parametrize("h,w,B", CAM_CASES)
+def test_contextual_attention_fp32_split_gemm(h, w, B):
+    """precision='fp32' without the attention-map output: the split-half fp16 tcgen05 GEMM attention (se_gemm_split.cu), which the
+    fp32-on-tensor-cores forward uses; same tolerance as the CUDA-core fp32 attention above."""
+    feat = F.relu(rand_act((B, 96, h, w), seed=h * w))
+    mask = torch.zeros(B, 1, 4 * h, 4 * w)
+    mask[:, :, h:3 * h, w:2 * w + 8] = 1.0
+    mask_s = F.avg_pool2d(mask, 4, 4)
+    from sketchedit_b200.engine import contextual_attention
+    out = contextual_attention(feat.cuda(), mask_s.cuda(), precision="fp32")
+    ref, _ = O.contextual_attention(feat, mask_s)
+    assert maxdiff(out.cpu(), ref) <= 2e-4 * max(1.0, float(ref.abs().max())), (maxdiff(out.cpu(), ref), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("h,w,B", CAM_CASES)
 def test_contextual_attention_bf16(h, w, B):
     # soft attention (small features) so bf16 logits cannot flip a hard arg-max
     feat = F.relu(rand_act((B, 96, h, w), seed=h * w + 1, scale=0.15))
