@@ -223,7 +223,7 @@ def roofline_from_classes(classes, steps, peaks, src, step_ms):
     ach_exec = tc_fe / tc_ms if tc_ms else 0.0
     dom = tc[0] if tc else None
     roof = {
-        "bound": "tensor", "kernel": "all tcgen05 implicit-GEMM launches (conv_c8_kernel / conv_tc_kernel classes: gated convs + attention GEMMs)",
+        "bound": "tensor", "kernel": "all tcgen05 launches (conv_c8_kernel classes: gated convs; cam_s / cam_pv or gemm_split: attention GEMMs)",
         "achieved": ach_alg, "achieved_executed": ach_exec, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_alg / peak_tf,
         "frac_executed": ach_exec / peak_tf,
         "flops_convention": "achieved = ALGORITHMIC 2*MAC of the reference ops the forward executes (SURVEY.md 8d; mode='inference' skips the dead netM "
