@@ -127,7 +127,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kPair ? 2 * 4 * epi_split : 128 * epi_split);   // pair: one arrive per epilogue warp of both CTAs
+      mbar_init(&tmem_empty[i], (kPair ? 2 : 1) * 4 * epi_split);   // one arrive per epilogue warp (pair: of both CTAs)
     }
     mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -446,11 +446,11 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
       else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
       tc_fence_before();
-      if (kPair) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0));   // the leader's MMA warp owns both accumulators
-      } else {
-        mbar_arrive(&tmem_empty[as]);
+      __syncwarp();
+      // ONE arrival per warp: 128 per-thread arrivals on the same barrier are serialised shared-memory atomics, paid per tile
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0));   // the leader's MMA warp owns both accumulators
+        else mbar_arrive(&tmem_empty[as]);
       }
     }
     if (p.dbg && threadIdx.x == 128) { p.dbg[blockIdx.x * 8 + 5] = t_wacc; p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin; }

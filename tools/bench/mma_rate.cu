@@ -101,6 +101,17 @@ __global__ void __launch_bounds__(384, 1) mma_rate(int N, int reps, int mode, in
     mbar_wait(&bar, 0, 99);
     const long long t2 = clock64();
     if (threadIdx.x == 0) { out[blockIdx.x * 4] = t1 - t0; out[blockIdx.x * 4 + 1] = t2 - t0; done = 1; }
+  } else if (warp >= 4 && ld_mode == 64) {
+    // does a saturated MMA issuer (warp 0, scheduler 0) slow down ALU work of the warps that share its scheduler?
+    // every warp runs the same dependent FMA chain until the issuer is done; out[8 + warp] = iterations completed
+    float acc = (float)threadIdx.x;
+    unsigned long long n = 0;
+    while (!done) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc = fmaf(acc, 1.0001f, 0.5f);
+      ++n;
+    }
+    if ((threadIdx.x & 31) == 0) { out[blockIdx.x * 32 + 8 + warp] = n; if (acc == 123.0f) out[0] = 1; }
   } else if (warp >= 4 && ld_mode) {
     // epilogue-like TMEM readers on accumulator columns 256.. (not written by the MMAs)
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
@@ -137,6 +148,21 @@ int main() {
       printf("concurrent tcgen05.ld.x%-2d by 8 warps  N=%3d  MMA %.1f cyc (ideal %d)   loads per warp during run: %llu  (= 1 per %.0f cyc)\n", ld, N,
              (double)h[1] / (reps * 4), N / 2 > 40 ? N / 2 : 40, h[2], h[2] ? (double)h[1] / h[2] : 0.0);
     }
+  {
+    unsigned long long* d2;
+    cudaMalloc(&d2, 148 * 32 * 8);
+    for (int N : {32, 96, 256}) {
+      cudaMemset(d2, 0, 148 * 32 * 8);
+      mma_rate<<<1, 384, 160 * 1024>>>(N, reps * 8, 0, 0, 0, 64, d2);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("scheduler test: %s\n", cudaGetErrorString(e)); return 1; }
+      unsigned long long h[32];
+      cudaMemcpy(h, d2, 256, cudaMemcpyDeviceToHost);
+      printf("issuer on scheduler 0, N=%3d, %.1f cyc/MMA: FMA-chain iterations of warps 4..11 (scheduler = warp %% 4):", N, (double)h[1] / (reps * 8 * 4));
+      for (int w = 4; w < 12; ++w) printf(" %llu", h[8 + w]);
+      printf("\n");
+    }
+  }
   for (int N : {32, 48, 96})
     for (int nacc : {1, 2, 4})
       for (int bsh : {0, 1, 3, 4}) {
