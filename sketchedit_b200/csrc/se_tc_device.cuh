@@ -181,8 +181,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// RELAXED: every use signals "this accumulator stage has been drained" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it);
+// nothing in generic memory is published by it. The default .release at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. the
+// epilogue warp sat until its output stores were visible GPU-wide before the MMA warp could get the TMEM stage back (ncu: 9 % of
+// all warp samples of the CTA-pair kernels).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // loads into OWN shared memory, completion bytes signalled on a (possibly remote) barrier of the CTA pair
 __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
