@@ -27,6 +27,17 @@
 
 namespace se {
 
+// SE_TC_DEBUG=2: per-tile timeline of CTA 0 (first 64 tiles of the non-fused resident path): dbg[2048 + iter * 8 + k] = clock64() at
+//   k = 0 halo TMA issued, 1 issuer has the TMEM stage, 2 issuer has the halo (MMAs start), 3 MMAs + commits issued,
+//   4 epilogue sees the accumulator, 5 TMEM drained + math + stores issued, 6 stage released
+// Compiled in only with -DSE_C8_TRACE (SE_NVCC_EXTRA="-DSE_C8_TRACE" python -m sketchedit_b200.build --force): the extra live values cost
+// the 96-register kernels 4-10 % on the small layers.
+#ifdef SE_C8_TRACE
+#define C8_TRACE(iter_, k_) do { if (p.dbg && p.trace && blockIdx.x == 0 && (iter_) < 64 && lane == 0) p.dbg[2048 + (iter_) * 8 + (k_)] = clock64(); } while (0)
+#else
+#define C8_TRACE(iter_, k_) do { } while (0)
+#endif
+
 constexpr int C8_TH = 16, C8_TW = 8;   // output tile: 16 rows x 8 columns = 128 positions
 
 // no-swizzle K-major operand: core matrices of 8 rows x 16 B; LBO = next core matrix along K, SBO = along M
@@ -195,6 +206,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
+        C8_TRACE(iter, 0);
       }
       if (staged) {
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -318,6 +330,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         long long tw = p.dbg ? clock64() : 0;
         if (kPair) mbar_wait_cluster(&tmem_empty[as], accphase ^ 1, 2); else mbar_wait(&tmem_empty[as], accphase ^ 1, 2);
         if (p.dbg) t_wtmem += clock64() - tw;
+        C8_TRACE(iter, 1);
         int ab = 0;
         if (halo) {
           uint32_t aph;
@@ -326,6 +339,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&a_full[ab], aph, 7);
           if (p.dbg) t_whalo += clock64() - tw;
         }
+        C8_TRACE(iter, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * acc_stride;
         for (int ks = 0; ks < (KS1 ? 1 : ksteps); ++ks) {
@@ -395,6 +409,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (staged && ++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
+        C8_TRACE(iter, 3);
       }
       }   // NCLS == 1
 
@@ -413,11 +428,15 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     long long t_wacc = 0, t_begin = clock64();
     // tile-alternating groups (epi_split == 1) visit every TC_EPI_GROUPS-th tile of this CTA; a tile's coordinates
     // come from two unsigned divisions (cheaper than stepping the mixed-radix counter through the skipped tiles)
-    const int istep = (epi_split == 1) ? TC_EPI_GROUPS : 1;
+    // Epilogue groups work in TEAMS of epi_split groups: a team drains one tile together (its groups take alternate column blocks),
+    // the TC_EPI_GROUPS / epi_split teams take alternate tiles. epi_split = 1: four one-group teams (N <= 128: one or two TMEM
+    // stages per group); 4: one team (N = 192, two stages); 2: two teams (experiment, see the launcher).
+    const int nteams = TC_EPI_GROUPS / epi_split, team = grp / epi_split, sub = grp - team * epi_split;
+    const int istep = nteams;
     const uint32_t tpi = (uint32_t)(p.tiles_x * p.tiles_y);
     // fused classes: `iter` counts VIRTUAL tiles (tile * NCLS + class); the launcher guarantees epi_split == 1 for them
     constexpr int CSH = NCLS == 4 ? 2 : (NCLS == 2 ? 1 : 0);
-    for (int iter = (epi_split == 1) ? grp : 0, tile = blockIdx.x + (iter >> CSH) * gridDim.x; tile < total_tiles;
+    for (int iter = team, tile = blockIdx.x + (iter >> CSH) * gridDim.x; tile < total_tiles;
          iter += istep, tile = blockIdx.x + (iter >> CSH) * gridDim.x) {
       const int cls = iter & (NCLS - 1);
       const uint32_t img_u = (uint32_t)tile / tpi, rem = (uint32_t)tile - img_u * tpi;
@@ -429,6 +448,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long tw = p.dbg ? clock64() : 0;
       mbar_wait(&tmem_full[as], accphase, 4);
       if (p.dbg) t_wacc += clock64() - tw;
+      if (q == 0) C8_TRACE(iter, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_stride;
       const int py = ty * C8_TH + ry, px = tx * C8_TW + rx;
@@ -436,15 +456,21 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // output pixel of this position (sub-pixel classes: osy = osx = 2 and a per-class offset)
       const int oy = py * p.e.osy + (NCLS > 1 ? p.cls_ooy[cls] : p.e.ooy), ox = px * p.e.osx + (NCLS > 1 ? p.cls_oox[cls] : p.e.oox);
       if (p.e.nsplit > 1) {     // split-half output (fp32-on-tensor-cores mode): exact-math gate, hi / lo stores
-        if (p.e.epi == EPI_GATE_ELU) tc_epilogue_gated_split<true>(p.e, bias_s, cst_n, taddr, img, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
-        else tc_epilogue_gated_split<false>(p.e, bias_s, cst_n, taddr, img, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
+        if (p.e.epi == EPI_GATE_ELU) tc_epilogue_gated_split<true>(p.e, bias_s, cst_n, taddr, img, valid, oy, ox, sub, epi_split);
+        else tc_epilogue_gated_split<false>(p.e, bias_s, cst_n, taddr, img, valid, oy, ox, sub, epi_split);
       } else if (KS1 && p.ecst_nb) {   // (only the single-k-step instantiations carry this code: the launcher sets ecst_nb for them alone)
         // constants as kernel parameters (gated, bf16 block output, 2 or 3 blocks, one group per tile)
         const bool elu = (p.e.epi == EPI_GATE_ELU);
-        if (p.ecst_nb == 3) { if (elu) tc_epilogue_gated_const<true, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); else tc_epilogue_gated_const<false, 3>(p.e, p.ecst, taddr, img, valid, oy, ox); }
-        else { if (elu) tc_epilogue_gated_const<true, 2>(p.e, p.ecst, taddr, img, valid, oy, ox); else tc_epilogue_gated_const<false, 2>(p.e, p.ecst, taddr, img, valid, oy, ox); }
-      } else if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
-      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, epi_split == 1 ? 0 : grp, epi_split);
+#ifdef SE_C8_TRACE
+        unsigned long long* tr = (p.dbg && p.trace && blockIdx.x == 0 && iter < 64 && lane == 0 && q == 0) ? &p.dbg[2048 + iter * 8 + 7] : nullptr;
+#else
+        constexpr unsigned long long* tr = nullptr;
+#endif
+        if (p.ecst_nb == 3) { if (elu) tc_epilogue_gated_const<true, 3>(p.e, p.ecst, taddr, img, valid, oy, ox, tr); else tc_epilogue_gated_const<false, 3>(p.e, p.ecst, taddr, img, valid, oy, ox, tr); }
+        else { if (elu) tc_epilogue_gated_const<true, 2>(p.e, p.ecst, taddr, img, valid, oy, ox, tr); else tc_epilogue_gated_const<false, 2>(p.e, p.ecst, taddr, img, valid, oy, ox, tr); }
+      } else if (fast_epi) tc_epilogue_tile<true>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, sub, epi_split);
+      else tc_epilogue_tile<false>(p.e, bias_s, cst_n, taddr, img, 0, valid, oy, ox, sub, epi_split);
+      if (q == 0) C8_TRACE(iter, 5);
       tc_fence_before();
       __syncwarp();
       // ONE arrival per warp: 128 per-thread arrivals on the same barrier are serialised shared-memory atomics, paid per tile
@@ -452,6 +478,7 @@ conv_c8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kPair) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[as]), 0));   // the leader's MMA warp owns both accumulators
         else mbar_arrive(&tmem_empty[as]);
       }
+      if (q == 0) C8_TRACE(iter, 6);
     }
     if (p.dbg && threadIdx.x == 128) { p.dbg[blockIdx.x * 8 + 5] = t_wacc; p.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin; }
   }
@@ -522,6 +549,7 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
   const int HR = C8_TH + (mx_y - mn_y), WR = C8_TW + (mx_x - mn_x) + extra_x;
   TcWeights& w = L->w;
   w.ntaps = ntaps;
+  L->mmas64 = (stem || Ci == 48) ? 3 : 4;   // 48 channels = three K16 slices of the one 64-wide unit: the fourth would multiply padding
   if (stem) { w.n64 = 1; w.n32 = 0; }
   else {
     w.n64 = Ci / 64;
@@ -569,15 +597,15 @@ int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int 
 }
 
 // the k-step structures of the generator's layers get their own fully unrolled instantiation
-#define C8_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(1, 0, 4) X(1, 1, 4) X(4, 4, 4) X(4, 0, 4) X(0, 3, 4) X(0, 1, 4) X(3, 0, 4)
+#define C8_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(9, 0, 3) X(1, 0, 4) X(1, 0, 3) X(1, 1, 4) X(4, 4, 4) X(4, 0, 4) X(4, 0, 3) X(0, 3, 4) X(0, 1, 4) X(3, 0, 4) X(3, 0, 3)
 // k-step structures of the streamed-weight layers that run as CTA pairs (96->192: <1,1>; 192/48->192: <1,0>;
 // the 48->96 stride-2 layer of the refine branch: <3,0>)
-#define C8_PAIR_SPECIALISATIONS(X) X(1, 0, 4) X(1, 1, 4) X(3, 0, 4)
+#define C8_PAIR_SPECIALISATIONS(X) X(1, 0, 4) X(1, 0, 3) X(1, 1, 4) X(3, 0, 4) X(3, 0, 3)
 // structures that occur with a single k-step per tile (resident weights): compile-time k-step index (KS1)
-#define C8_KS1_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(4, 4, 4) X(4, 0, 4)
+#define C8_KS1_SPECIALISATIONS(X) X(5, 0, 3) X(0, 9, 4) X(9, 0, 4) X(9, 0, 3) X(4, 4, 4) X(4, 0, 4) X(4, 0, 3)
 // fused sub-pixel classes of the two deconv shapes: 48->48 (one 64-channel unit per tap, all 4 classes resident) and
 // 96->96 (64 + 32 channel units per tap, 2 classes resident: one launch per output-row parity)
-#define C8_GROUP_SPECIALISATIONS(X) X(4, 0, 4, 4) X(4, 4, 4, 2) X(4, 0, 4, 2) X(4, 4, 4, 4)
+#define C8_GROUP_SPECIALISATIONS(X) X(4, 0, 4, 4) X(4, 0, 3, 4) X(4, 4, 4, 2) X(4, 0, 4, 2) X(4, 0, 3, 2) X(4, 4, 4, 4)
 static int c8_set_smem_attr(int bytes) {
 #define X(a, b, m) SE_CUDA_OK(cudaFuncSetAttribute(conv_c8_kernel<a, b, m, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   C8_SPECIALISATIONS(X)
@@ -620,7 +648,7 @@ static int c8_dispatch(const C8Params& p, const CUtensorMap& tmA, const CUtensor
   }
   if (p.ncls > 1) {
 #define X(a, b, m, n)                                                                             \
-    if (p.r64 == a && p.r32 == b && p.ncls == n) {                                                 \
+    if (p.r64 == a && p.r32 == b && p.ncls == n && p.mmas64 == m) {                                \
       conv_c8_kernel<a, b, m, 0, 1, n><<<grid, TC_NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p); \
       return 0;                                                                                   \
     }
@@ -650,8 +678,8 @@ static int c8_dispatch(const C8Params& p, const CUtensorMap& tmA, const CUtensor
 }
 
 static const int kGroupSmemMax = 222 * 1024;   // fused classes may use (almost) the whole opt-in window: weights of all classes + 2 halos
-static bool c8_group_kernel_exists(int r64, int r32, int ncls) {
-#define X(a, b, m, n) if (r64 == a && r32 == b && ncls == n) return true;
+static bool c8_group_kernel_exists(int r64, int r32, int ncls, int mmas64) {
+#define X(a, b, m, n) if (r64 == a && r32 == b && ncls == n && mmas64 == m) return true;
   C8_GROUP_SPECIALISATIONS(X)
 #undef X
   return false;
@@ -679,7 +707,8 @@ int c8_configure_group(C8Group* G, int ncls, int ntaps, const int8_t (*dy)[8], c
   w.img_bytes = 0;
   w.r64 = ntaps * w.n64;      // resident weights + halo: one k-step issues every MMA of a (tile, class)
   w.r32 = ntaps * w.n32;
-  if (w.r64 + w.r32 > C8_CLS_UNITS || !c8_group_kernel_exists(w.r64, w.r32, ncls)) return 1;
+  L.mmas64 = Ci == 48 ? 3 : 4;
+  if (w.r64 + w.r32 > C8_CLS_UNITS || !c8_group_kernel_exists(w.r64, w.r32, ncls, L.mmas64)) return 1;
   L.mode = C8_HALO;
   L.resident = true;
   L.stem = false;
@@ -706,7 +735,7 @@ bool c8_pair_capable(const C8Layer& L) {
   const TcWeights& w = L.w;
   if (off || L.resident || L.stem || w.NT % 32 != 0) return false;
   const int half_bytes = (w.NT / 2) * (w.r64 * 128 + w.r32 * 64);
-  return half_bytes % 512 == 0 && c8_pair_kernel_exists(w.n64 ? w.r64 : 0, w.n32 ? w.r32 : 0, 4);
+  return half_bytes % 512 == 0 && c8_pair_kernel_exists(w.n64 ? w.r64 : 0, w.n32 ? w.r32 : 0, L.mmas64);
 }
 
 int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, const C8Group* grp) {
@@ -741,7 +770,7 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
   p.cls_bytes = grp ? grp->cls_bytes : 0;
   for (int k = 0; k < C8_MAX_CLS; ++k) { p.cls_ooy[k] = grp && k < grp->ncls ? grp->ooy[k] : 0; p.cls_oox[k] = grp && k < grp->ncls ? grp->oox[k] : 0; }
   if (L.stem) { p.lbo_bytes = 16; p.kstep_bytes = 32; p.mmas64 = 3; }
-  else { p.lbo_bytes = L.HR * L.WR * 16; p.kstep_bytes = 2 * p.lbo_bytes; p.mmas64 = 4; }
+  else { p.lbo_bytes = L.HR * L.WR * 16; p.kstep_bytes = 2 * p.lbo_bytes; p.mmas64 = L.mmas64; }
   p.sbo_bytes = L.WR * 16;
   p.bias = c.bias;
   fill_epi(c, w.NT, &p.e);
@@ -804,7 +833,10 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
   p.a_bufs = 2;
   p.niss = 1;
   p.acc_stages = w.NT <= 64 ? 8 : (w.NT <= 128 ? 4 : 2);
-  p.epi_split = w.NT <= 128 ? 1 : TC_EPI_GROUPS;
+  // groups per tile (teams, see the epilogue loop). Two-group teams for 64 < N <= 128 measured SLOWER than one group per tile (stem
+  // pair 916 -> 1040-1096 us, 48->96 787 -> 809-818 us per step at the bench shape): SE_C8_TEAMS=1 is an experiment switch only.
+  static const bool teams_on = getenv("SE_C8_TEAMS") != nullptr && atoi(getenv("SE_C8_TEAMS")) != 0;
+  p.epi_split = w.NT <= 64 ? 1 : (w.NT <= 128 ? ((teams_on && !grp) ? 2 : 1) : TC_EPI_GROUPS);
   if (L.mode == C8_HALO) {
     if (fixed + 2 * L.a_bytes + 3 * stage_bytes > smem_budget) p.a_bufs = 1;   // measured: 2 halo buffers + 3 weight stages beats 1 + 4
     // nothing streamed: a tile is short (700-2000 cycles of MMAs) against a TMA round trip of ~1500 cycles, so two
@@ -883,9 +915,14 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
   static const bool dbg_on = getenv("SE_TC_DEBUG") != nullptr;
   static unsigned long long* dbg_buf = nullptr;
   if (dbg_on) {
-    if (!dbg_buf) SE_CUDA_OK(cudaMalloc(&dbg_buf, 8 * 8 * 1024));
-    SE_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 8 * 8 * 1024, stream));
+    if (!dbg_buf) SE_CUDA_OK(cudaMalloc(&dbg_buf, 8 * 4096));
+    SE_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 8 * 4096, stream));
     p.dbg = dbg_buf;
+#ifdef SE_C8_TRACE
+    p.trace = atoi(getenv("SE_TC_DEBUG")) >= 2 ? 1 : 0;
+#else
+    p.trace = 0;
+#endif
   }
   { int rc_launch = c8_dispatch(p, tmA, tmB, pair, grid, smem_bytes, stream); if (rc_launch) return rc_launch; }
   SE_CUDA_OK(cudaGetLastError());
@@ -900,6 +937,19 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
             "[c8] N=%d %dx%d Ci=%d taps=%d NT=%d mode=%s pair=%d res=%d HRxWR=%dx%d abufs=%d n64=%d n32=%d r64=%d r32=%d stages=%d tiles=%d | prod wait %.0f/%.0f | mma wait_full %.0f wait_halo %.0f wait_tmem %.0f /%.0f | epi wait_acc %.0f/%.0f\n",
             c.N, c.Ho, c.Wo, c.Ci, c.ntaps, p.NT, L.mode == C8_HALO ? "halo" : "pertap", (int)pair, p.resident, L.HR, L.WR, p.a_bufs, p.n64, p.n32, p.r64, p.r32,
             p.num_stages, total_tiles, a[0], a[1], a[2], a[7], a[3], a[4], a[5], a[6]);
+    if (p.trace) {
+      std::vector<unsigned long long> t(64 * 8);
+      SE_CUDA_OK(cudaMemcpy(t.data(), dbg_buf + 2048, t.size() * 8, cudaMemcpyDeviceToHost));
+      unsigned long long t0 = ~0ull;
+      for (auto v : t) if (v && v < t0) t0 = v;
+      fprintf(stderr, "[c8 trace] CTA 0, cycles since its first event: iter | tma_issued | got_tmem got_halo mma_issued | acc_seen epi_done released | tmem_loaded   (acc_stages=%d niss=%d abufs=%d)\n",
+              p.acc_stages, p.niss, p.a_bufs);
+      for (int i = 0; i < 64 && i * (int)(grid) < total_tiles; ++i) {
+        fprintf(stderr, "[c8 trace] %2d |", i);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld%s", t[i * 8 + k] ? (long long)(t[i * 8 + k] - t0) : -1LL, (k == 0 || k == 3 || k == 6) ? " |" : "");
+        fprintf(stderr, "\n");
+      }
+    }
   }
   return 0;
 }

@@ -16,6 +16,7 @@ struct C8Layer {
   bool resident = false;
   bool stem = false;    // GEMM-K walks the pixel window of the 8-channel packed input
   int cb_in = 0;        // channel blocks read
+  int mmas64 = 4;       // K16 MMAs per 64-channel unit: 3 when the layer has 48 input channels (the unit's last 16 are padding), 3 for stems
   int HR = 0, WR = 0;   // rows / columns of the shared-memory A region
   int pad_y0 = 0, pad_x0 = 0;
   int a_bytes = 0, a_tx_bytes = 0;
@@ -67,6 +68,7 @@ struct C8Params {
   int ncls, cls_bytes;            // fused deconv classes (C8Group): classes per tile, bytes between their weight images
   int cls_ooy[C8_MAX_CLS], cls_oox[C8_MAX_CLS];
   unsigned long long* dbg;
+  int trace;   // SE_TC_DEBUG=2: per-tile timeline of CTA 0 (C8_TRACE)
 };
 
 int c8_configure(C8Layer* L, int ntaps, const int8_t* dy, const int8_t* dx, int Ci, int Cout, bool stem, const int8_t* tap_cb = nullptr);

@@ -552,7 +552,7 @@ __device__ __forceinline__ void tc_epilogue_gated_split(const EpiParams& e, cons
 // All TMEM loads of the tile are issued before the single wait.
 template <bool kElu, int NB>
 __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, const float (&cst)[3][24], uint32_t taddr, int img, bool valid, int oy,
-                                                        int ox) {
+                                                        int ox, unsigned long long* trace = nullptr) {
   const int goff = e.goff;
   uint4* const ybase = reinterpret_cast<uint4*>(e.y);
   uint32_t obase, ostep;
@@ -578,6 +578,7 @@ __device__ __forceinline__ void tc_epilogue_gated_const(const EpiParams& e, cons
       tmem_ld8(taddr + goff + (b0 + j) * 8, g[j]);
     }
     tmem_ld_wait();
+    if (trace) *trace = clock64();
     if (valid) {
 #pragma unroll
       for (int j = 0; j < PASS; ++j) {
