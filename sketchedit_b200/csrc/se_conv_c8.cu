@@ -854,6 +854,16 @@ int c8_launch(const ConvParams& c, const C8Layer& L_in, cudaStream_t stream, con
     fixed += p.a_bufs * L.a_bytes;
   }
   p.acc_stride = w.NT <= 64 ? 64 : (w.NT <= 128 ? 128 : 256);
+  // N = 96 resident layers (stem pairs, 48->96, 24->96): four 128-column stages are one per epilogue group, so a group's cycle is
+  // drain (4000-5000 cycles) + refill (TMA wait + MMAs + completion, ~2400) with nothing overlapped (tile timelines).
+  // FIVE stages of 96 columns rotate one spare stage through the four groups: the tile a group takes next is already being
+  // filled while it drains. Stage ownership is then shared, which is only safe with ONE in-order issuer (se_conv_c8.cu header).
+  static const bool five_on = getenv("SE_C8_FIVE") != nullptr && atoi(getenv("SE_C8_FIVE")) != 0;
+  if (five_on && !grp && !pair && stage_bytes == 0 && L.mode == C8_HALO && w.NT == 96 && p.epi_split == 1) {
+    p.acc_stages = 5;
+    p.acc_stride = 96;
+    p.niss = 1;
+  }
   p.a_shift = -1;
   for (int sh = 0; sh < 4; ++sh) if ((1 << sh) == p.a_bufs) p.a_shift = sh;
   p.acc_shift = -1;
