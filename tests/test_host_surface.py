@@ -96,3 +96,27 @@ def test_testimage_dataset_reads_the_reference_list_format(tmp_path):
         seen.append(n)
     assert seen == names                                  # serial_batches: list order
     assert os.path.isdir(odir)
+
+
+def test_bench_roofline_math_from_class_table():
+    """bench.py's roofline block is recomputable from its per-class rows: frac = sum(algorithmic FLOPs of the tcgen05 classes) / sum(their
+    time) / peak; a class is 'hbm' bound when its bytes / HBM peak exceed its FLOPs / tensor peak; per-layer frac = sum(ideal) / sum(time)."""
+    import bench
+    peaks = {"hbm_gbs": 6000.0, "bf16_tflops": 1700.0, "bf16_tflops_sustained": 1500.0}
+    classes = [
+        {"name": "conv_c8_kernel|big", "tensor": 1, "launches": 20, "ms": 2 * 1.0, "flops_alg": 2 * 1.2e12, "flops_exec": 2 * 1.0e12, "bytes_alg": 2 * 1.0e8},
+        {"name": "conv_c8_kernel|small", "tensor": 1, "launches": 4, "ms": 2 * 0.5, "flops_alg": 2 * 0.03e12, "flops_exec": 2 * 0.03e12, "bytes_alg": 2 * 1.2e9},
+        {"name": "pack8_kernel|glue", "tensor": 0, "launches": 2, "ms": 2 * 0.1, "flops_alg": 0.0, "flops_exec": 0.0, "bytes_alg": 2 * 3.0e8},
+    ]
+    roof, rows = bench.roofline_from_classes(classes, 2, peaks, "test", 2.0)
+    by = {r["class"]: r for r in rows}
+    assert by["conv_c8_kernel|big"]["bound"] == "tensor" and abs(by["conv_c8_kernel|big"]["frac"] - 1.2e12 / 1500e12 / 1e-3) < 1e-9
+    assert by["conv_c8_kernel|small"]["bound"] == "hbm" and abs(by["conv_c8_kernel|small"]["frac"] - (1.2e9 / 6000e9) / 0.5e-3) < 1e-9
+    assert by["pack8_kernel|glue"]["bound"] == "hbm"
+    tc_ms = 1.0 + 0.5
+    assert abs(roof["achieved"] - (1.2e12 + 0.03e12) / (tc_ms * 1e-3) / 1e12) < 1e-6
+    assert abs(roof["frac"] - roof["achieved"] / 1500.0) < 1e-12 and roof["peak"] == 1500.0
+    assert abs(roof["kernel_share_of_step"] - tc_ms / 2.0) < 1e-12
+    ideal = 1.2e12 / 1500e12 * 1e3 + 1.2e9 / 6000e9 * 1e3 + 3.0e8 / 6000e9 * 1e3
+    assert abs(roof["per_layer_roofline_frac"] - ideal / 1.6) < 1e-9
+    assert roof["dominant"]["class"] == "conv_c8_kernel|big"
